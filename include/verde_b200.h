@@ -1,0 +1,135 @@
+/*
+ * verde_b200.h -- C ABI of the B200-native Green's-function spline engine.
+ *
+ * This is the drop-in boundary for ONE hot path of fatiando/verde: the numeric
+ * kernels under verde.Spline / verde.SplineCV / verde.VectorSpline2D.  The
+ * reference reaches that path through caller-allocates-output free functions on
+ * contiguous float64 1-D arrays (numba-jitted) plus `least_squares`; each entry
+ * point below names the reference function it replaces (paths relative to the
+ * reference checkout).  A maintainer binds them with ctypes exactly as
+ * INTEGRATION.md shows.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types; all arrays float64, contiguous.
+ *  - every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE
+ *    pointer of the current CUDA device; the library checks with
+ *    cudaPointerGetAttributes and stages host data itself.  The caller owns all
+ *    buffers, outputs are written in place.
+ *  - calls are synchronous: results are complete when the function returns.
+ *  - return value: 0 = ok; > 0 = numerical failure (1-based index of the first
+ *    non-positive Cholesky pivot, LAPACK `info` style); < 0 = VB200_E_* below.
+ *    Nothing throws across the ABI.  vb200_last_error() gives a message.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    returns VB200_E_CUDA.
+ */
+#ifndef VERDE_B200_H
+#define VERDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_E_BADARG (-1)
+#define VB200_E_CUDA (-2)
+#define VB200_E_NOMEM (-3)
+
+/* Diagnostics of one fit (all optional; pass NULL to skip). */
+typedef struct vb200_fit_info {
+    int32_t info;            /* 0, or 1-based index of the failed pivot                        */
+    int32_t block_rows;      /* T: 128-wide block rows of the padded normal matrix             */
+    int64_t rows;            /* rows of the least-squares system (n, or 2n for the 2-D spline) */
+    int64_t cols;            /* unknowns (m, or 2m)                                            */
+    double gram_ms;          /* device time: panel generation + Gram accumulation              */
+    double factor_ms;        /* device time: scaling + Cholesky                                */
+    double solve_ms;         /* device time: forward/back substitution + unscaling             */
+    double gemm_ms;          /* device time inside the DMMA tile kernel (all launches)         */
+    double gemm_flops;       /* algorithmic flops those launches performed (2*128^3 per tile-chunk) */
+    int64_t gemm_launches;   /* launches of the DMMA tile kernel                               */
+    int64_t kernel_launches; /* all kernel launches of this fit                                */
+    double diag_min;         /* min / max of diag(L)^2: a cheap conditioning indicator         */
+    double diag_max;
+} vb200_fit_info;
+
+/* ---- library / device -------------------------------------------------------------- */
+int vb200_version(void);
+const char *vb200_last_error(void);
+int vb200_device_count(void);
+int vb200_set_device(int device);
+/* tunables: "predict_exact" (0/1), "chol_panel_tiles" (1..16), "gram_slab_chunks" (1..16) */
+int vb200_set_option(const char *key, double value);
+/* frees the cached device workspace (Gram matrix, panels) */
+int vb200_release_workspace(void);
+
+/* ---- K0: Jacobian materialisation --------------------------------------------------- */
+/* replaces verde/spline.py:642-650 jacobian_numba(east, north, force_east, force_north,
+ * mindist, jac): jac is row-major (n, m). */
+int vb200_jacobian(const double *east, const double *north, int64_t n, const double *force_east,
+                   const double *force_north, int64_t m, double mindist, double *jac);
+/* replaces verde/vector.py:461-475 jacobian_2d_numba(..., mindist, poisson, jac):
+ * jac is row-major (2n, 2m) = [[ee, ne], [ne, nn]]. */
+int vb200_jacobian_2d(const double *east, const double *north, int64_t n,
+                      const double *force_east, const double *force_north, int64_t m,
+                      double mindist, double poisson, double *jac);
+
+/* ---- K3: matrix-free predict -------------------------------------------------------- */
+/* replaces verde/spline.py:629-639 predict_numba(east, north, force_east, force_north,
+ * mindist, forces, result). */
+int vb200_predict(const double *east, const double *north, int64_t n, const double *force_east,
+                  const double *force_north, const double *forces, int64_t m, double mindist,
+                  double *result);
+/* replaces verde/vector.py:443-458 predict_2d_numba(..., mindist, poisson, forces, vec_east,
+ * vec_north); forces has length 2m (east forces, then north forces). */
+int vb200_predict_2d(const double *east, const double *north, int64_t n,
+                     const double *force_east, const double *force_north, const double *forces,
+                     int64_t m, double mindist, double poisson, double *vec_east,
+                     double *vec_north);
+
+/* ---- K1 + K2: fused fit -------------------------------------------------------------- */
+/* replaces, in one call, verde/spline.py:462-463:
+ *     jacobian = self.jacobian(coordinates[:2], self.force_coords_)
+ *     self.force_ = least_squares(jacobian, data, weights, self.damping)
+ * (verde/base/least_squares.py:17-71, damped branch).  weights may be NULL.
+ * out_force has length m. */
+int vb200_spline_fit(const double *east, const double *north, const double *data,
+                     const double *weights, int64_t n, const double *force_east,
+                     const double *force_north, int64_t m, double mindist, double damping,
+                     double *out_force, vb200_fit_info *info);
+/* replaces verde/vector.py:287-288 for VectorSpline2D.  data / weights have length 2n (east
+ * components then north components, verde/vector.py:279-284); out_force has length 2m. */
+int vb200_spline_fit_2d(const double *east, const double *north, const double *data,
+                        const double *weights, int64_t n, const double *force_east,
+                        const double *force_north, int64_t m, double mindist, double poisson,
+                        double damping, double *out_force, vb200_fit_info *info);
+
+/* ---- staged fit, for row-sharded multi-GPU and for SplineCV's damping sweeps -------------
+ * gram:   accumulates this rank's rows into G (tile-packed lower triangle, DEVICE memory,
+ *         vb200_gram_doubles(cols) doubles) and stats (DEVICE, vb200_stats_doubles(cols)
+ *         doubles = {J^T W d, J^T 1, diag(J^T J), reserved}).  accumulate = 0 overwrites.
+ *         kind 0 = scalar spline, 1 = 2-D elastic spline.
+ * (the caller all-reduces G and stats across ranks: both are plain sums over data rows)
+ * solve:  scales (StandardScaler algebra), adds damping, factors and solves.  G is destroyed
+ *         unless keep_gram != 0 (then a device copy is factored instead).  total_rows is the
+ *         number of system rows summed over all ranks. */
+int64_t vb200_gram_doubles(int64_t cols);
+int64_t vb200_stats_doubles(int64_t cols);
+int vb200_gram_accumulate(int kind, const double *east, const double *north, const double *data,
+                          const double *weights, int64_t n, const double *force_east,
+                          const double *force_north, int64_t m, double mindist, double poisson,
+                          double *gram_dev, double *stats_dev, int accumulate,
+                          vb200_fit_info *info);
+int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
+                     double damping, int keep_gram, double *out_params, vb200_fit_info *info);
+
+/* ---- least squares on an explicit Jacobian ----------------------------------------------
+ * replaces verde/base/least_squares.py:17 least_squares(jacobian, data, weights, damping):
+ * jac row-major (n, m); damped branch only (damping > 0). */
+int vb200_least_squares(const double *jac, int64_t n, int64_t m, const double *data,
+                        const double *weights, double damping, double *out_params,
+                        vb200_fit_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VERDE_B200_H */

@@ -1,0 +1,132 @@
+"""
+ctypes binding of ``libverde_b200.so`` (the C ABI in ``include/verde_b200.h``).
+
+This module is deliberately thin: numpy arrays (or raw device pointers) in,
+status codes out.  There is NO CPU fallback -- if the shared library is missing
+or no CUDA device is present every compute call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libverde_b200.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+i64 = ctypes.c_int64
+dbl = ctypes.c_double
+
+E_BADARG, E_CUDA, E_NOMEM = -1, -2, -3
+
+
+class FitInfo(ctypes.Structure):
+    """Mirror of ``vb200_fit_info`` (include/verde_b200.h)."""
+
+    _fields_ = [
+        ("info", ctypes.c_int32),
+        ("block_rows", ctypes.c_int32),
+        ("rows", ctypes.c_int64),
+        ("cols", ctypes.c_int64),
+        ("gram_ms", ctypes.c_double),
+        ("factor_ms", ctypes.c_double),
+        ("solve_ms", ctypes.c_double),
+        ("gemm_ms", ctypes.c_double),
+        ("gemm_flops", ctypes.c_double),
+        ("gemm_launches", ctypes.c_int64),
+        ("kernel_launches", ctypes.c_int64),
+        ("diag_min", ctypes.c_double),
+        ("diag_max", ctypes.c_double),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# name -> (restype, argtypes); the single source of truth for the symbol check in
+# tests/test_cabi_symbols.py (must match include/verde_b200.h)
+SIGNATURES = {
+    "vb200_version": (ctypes.c_int, []),
+    "vb200_last_error": (ctypes.c_char_p, []),
+    "vb200_device_count": (ctypes.c_int, []),
+    "vb200_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "vb200_set_option": (ctypes.c_int, [ctypes.c_char_p, dbl]),
+    "vb200_release_workspace": (ctypes.c_int, []),
+    "vb200_jacobian": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, ctypes.c_void_p]),
+    "vb200_jacobian_2d": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, ctypes.c_void_p]),
+    "vb200_predict": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 3 + [i64, dbl, ctypes.c_void_p]),
+    "vb200_predict_2d": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 3 + [i64, dbl, dbl] + [ctypes.c_void_p] * 2),
+    "vb200_spline_fit": (ctypes.c_int, [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+    "vb200_spline_fit_2d": (ctypes.c_int, [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+    "vb200_gram_doubles": (i64, [i64]),
+    "vb200_stats_doubles": (i64, [i64]),
+    "vb200_gram_accumulate": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl] + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.POINTER(FitInfo)]),
+    "vb200_gram_solve": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+    "vb200_least_squares": (ctypes.c_int, [ctypes.c_void_p, i64, i64] + [ctypes.c_void_p] * 2 + [dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """The CUDA engine is missing or reported a CUDA/argument error."""
+
+
+def load():
+    """Load the shared library (raises EngineError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                "verde_b200 CUDA library not built: {} is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU "
+                "fallback).".format(LIB_PATH)
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def require_device():
+    lib = load()
+    if lib.vb200_device_count() < 1:
+        raise EngineError("verde_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback")
+    return lib
+
+
+def ptr(a):
+    """void* of a numpy array, a torch CUDA tensor, an int device address, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    raise TypeError("cannot take the address of {!r}".format(type(a)))
+
+
+def f64(a):
+    """Contiguous 1-D float64 view/copy of an array-like (host)."""
+    return np.ascontiguousarray(np.ravel(np.atleast_1d(np.asarray(a))), dtype=np.float64)
+
+
+def check(rc, what):
+    """Translate a status code: <0 -> EngineError, >0 -> LinAlgError, 0 -> ok."""
+    if rc == 0:
+        return
+    msg = load().vb200_last_error().decode("utf-8", "replace")
+    if rc > 0:
+        raise np.linalg.LinAlgError(
+            "{}: the damped normal matrix is not positive definite (pivot {}): {}".format(what, rc, msg)
+        )
+    if rc == E_NOMEM:
+        raise MemoryError("{}: out of device memory: {}".format(what, msg))
+    if rc == E_BADARG:
+        raise ValueError("{}: {}".format(what, msg))
+    raise EngineError("{}: {}".format(what, msg))

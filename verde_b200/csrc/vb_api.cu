@@ -1,0 +1,589 @@
+// vb_api.cu -- the C ABI declared in include/verde_b200.h.
+//
+// Host orchestration only: staging of host buffers, the cached device
+// workspace, the slab loop of the Gram accumulation, CUDA-event timing for the
+// roofline report.  All arithmetic is in the kernels of vb_greens.cu,
+// vb_gram.cu, vb_gemm.cu and vb_chol.cu.
+#include "../../include/verde_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "vb_common.cuh"
+#include "vb_internal.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(e_ == cudaErrorMemoryAllocation ? VB200_E_NOMEM : VB200_E_CUDA,          \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- options -------------------------------------------------------------------------
+struct Options {
+    int predict_exact = 0;
+    int chol_panel_tiles = 4;
+    int gram_slab_chunks = 16;
+} g_opt;
+
+// ---- cached workspace (grow-only, per process; one process per GPU) --------------------
+struct Slot {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+std::map<std::string, Slot> g_ws;
+
+cudaError_t ws_get(const char *name, size_t bytes, void **out)
+{
+    Slot &s = g_ws[name];
+    if (s.bytes < bytes) {
+        if (s.ptr) cudaFree(s.ptr);
+        s.ptr = nullptr;
+        s.bytes = 0;
+        cudaError_t e = cudaMalloc(&s.ptr, bytes ? bytes : 8);
+        if (e != cudaSuccess) return e;
+        s.bytes = bytes ? bytes : 8;
+    }
+    *out = s.ptr;
+    return cudaSuccess;
+}
+
+bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Input staging: host pointers are copied into a named workspace slot.
+cudaError_t stage_in(const char *slot, const double *p, long long count, const double **dev,
+                     cudaStream_t st)
+{
+    if (p == nullptr || count == 0) {
+        *dev = nullptr;
+        return cudaSuccess;
+    }
+    if (is_device_ptr(p)) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    void *d;
+    cudaError_t e = ws_get(slot, sizeof(double) * count, &d);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(d, p, sizeof(double) * count, cudaMemcpyHostToDevice, st);
+    *dev = static_cast<const double *>(d);
+    return e;
+}
+
+struct OutBuf {
+    double *user = nullptr;
+    double *dev = nullptr;
+    long long count = 0;
+    bool staged = false;
+};
+
+cudaError_t stage_out(const char *slot, double *p, long long count, OutBuf *ob)
+{
+    ob->user = p;
+    ob->count = count;
+    if (count == 0) return cudaSuccess;
+    if (is_device_ptr(p)) {
+        ob->dev = p;
+        ob->staged = false;
+        return cudaSuccess;
+    }
+    void *d;
+    cudaError_t e = ws_get(slot, sizeof(double) * count, &d);
+    ob->dev = static_cast<double *>(d);
+    ob->staged = true;
+    return e;
+}
+
+cudaError_t finish_out(const OutBuf &ob, cudaStream_t st)
+{
+    if (ob.staged && ob.count)
+        return cudaMemcpyAsync(ob.user, ob.dev, sizeof(double) * ob.count, cudaMemcpyDeviceToHost, st);
+    return cudaSuccess;
+}
+
+// ---- event timing ------------------------------------------------------------------------
+struct Span {
+    cudaEvent_t a, b;
+};
+struct Profile {
+    std::vector<Span> gemm;
+    double gemm_flops = 0.0;
+    long long launches = 0;
+    bool on = false;
+} g_prof;
+
+cudaError_t span_begin(Span *s, cudaStream_t st)
+{
+    cudaError_t e = cudaEventCreate(&s->a);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreate(&s->b);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(s->a, st);
+}
+double span_ms(Span &s)
+{
+    float ms = 0.f;
+    cudaEventSynchronize(s.b);
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+    return ms;
+}
+
+cudaError_t timed_gemm(const VbGemmParams &p, cudaStream_t st)
+{
+    Span s;
+    cudaError_t e = span_begin(&s, st);
+    if (e != cudaSuccess) return e;
+    e = vb_launch_gemm(p, st);
+    cudaEventRecord(s.b, st);
+    g_prof.gemm.push_back(s);
+    g_prof.gemm_flops += 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
+    g_prof.launches += 1;
+    return e;
+}
+
+void prof_reset()
+{
+    g_prof.gemm.clear();
+    g_prof.gemm_flops = 0.0;
+    g_prof.launches = 0;
+}
+
+void prof_collect(vb200_fit_info *info)
+{
+    double ms = 0.0;
+    for (auto &s : g_prof.gemm) ms += span_ms(s);
+    if (info) {
+        info->gemm_ms += ms;
+        info->gemm_flops += g_prof.gemm_flops;
+        info->gemm_launches += g_prof.launches;
+    }
+    prof_reset();
+}
+
+__global__ void vb_unscale_kernel(const double *__restrict__ x, const double *__restrict__ inv_scale,
+                                  long long cols, double *__restrict__ out)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < cols) out[j] = x[j] * inv_scale[j];
+}
+
+// min / max of diag(L)^2 over the first `cols` unknowns (single CTA; T*128 values)
+__global__ void vb_diag_minmax_kernel(const double *__restrict__ L, int T, long long cols,
+                                      double *__restrict__ out2)
+{
+    __shared__ double smin[256], smax[256];
+    double lo = 1e300, hi = 0.0;
+    for (long long j = threadIdx.x; j < cols; j += blockDim.x) {
+        const int b = (int)(j / VB_TILE), c = (int)(j % VB_TILE);
+        const double d = L[vb_tile_index(b, b, T) * VB_TILE_ELEMS + c * VB_TILE + c];
+        const double v = d * d;
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    smin[threadIdx.x] = lo;
+    smax[threadIdx.x] = hi;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + s]);
+            smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out2[0] = smin[0];
+        out2[1] = smax[0];
+    }
+}
+
+}  // namespace
+
+// vb_chol.cu calls the GEMM through this hook so that its launches are timed too.
+cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t st) { return timed_gemm(p, st); }
+
+extern "C" {
+
+int vb200_version(void) { return 100; }
+const char *vb200_last_error(void) { return g_error.c_str(); }
+
+int vb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int vb200_set_device(int device)
+{
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+int vb200_set_option(const char *key, double value)
+{
+    if (!key) return fail(VB200_E_BADARG, "null option key");
+    const std::string k(key);
+    if (k == "predict_exact") g_opt.predict_exact = value != 0.0;
+    else if (k == "chol_panel_tiles") g_opt.chol_panel_tiles = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
+    else if (k == "gram_slab_chunks") g_opt.gram_slab_chunks = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
+    else return fail(VB200_E_BADARG, "unknown option '%s'", key);
+    return 0;
+}
+
+int vb200_release_workspace(void)
+{
+    for (auto &kv : g_ws)
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+    g_ws.clear();
+    return 0;
+}
+
+int vb200_jacobian(const double *east, const double *north, int64_t n, const double *force_east,
+                   const double *force_north, int64_t m, double mindist, double *jac)
+{
+    if (n < 0 || m < 0) return fail(VB200_E_BADARG, "negative size");
+    if (n == 0 || m == 0) return 0;
+    if (!east || !north || !force_east || !force_north || !jac) return fail(VB200_E_BADARG, "null pointer");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dfe, *dfn;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("in_fe", force_east, m, &dfe, st));
+    CU(stage_in("in_fn", force_north, m, &dfn, st));
+    OutBuf ob;
+    CU(stage_out("out_jac", jac, (long long)n * m, &ob));
+    CU(vb_launch_jacobian(de, dn, n, dfe, dfn, m, mindist, ob.dev, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vb200_jacobian_2d(const double *east, const double *north, int64_t n,
+                      const double *force_east, const double *force_north, int64_t m,
+                      double mindist, double poisson, double *jac)
+{
+    if (n < 0 || m < 0) return fail(VB200_E_BADARG, "negative size");
+    if (n == 0 || m == 0) return 0;
+    if (!east || !north || !force_east || !force_north || !jac) return fail(VB200_E_BADARG, "null pointer");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dfe, *dfn;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("in_fe", force_east, m, &dfe, st));
+    CU(stage_in("in_fn", force_north, m, &dfn, st));
+    OutBuf ob;
+    CU(stage_out("out_jac", jac, 4LL * n * m, &ob));
+    CU(vb_launch_jacobian2d(de, dn, n, dfe, dfn, m, mindist, poisson, ob.dev, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vb200_predict(const double *east, const double *north, int64_t n, const double *force_east,
+                  const double *force_north, const double *forces, int64_t m, double mindist,
+                  double *result)
+{
+    if (n < 0 || m < 0) return fail(VB200_E_BADARG, "negative size");
+    if (n == 0) return 0;
+    if (!east || !north || !result || (m > 0 && (!force_east || !force_north || !forces)))
+        return fail(VB200_E_BADARG, "null pointer");
+    if (m > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many forces");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dfe, *dfn, *df;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("in_fe", force_east, m, &dfe, st));
+    CU(stage_in("in_fn", force_north, m, &dfn, st));
+    CU(stage_in("in_f", forces, m, &df, st));
+    OutBuf ob;
+    CU(stage_out("out_pred", result, n, &ob));
+    int pts, nsplit;
+    vb_predict_plan(n, m, &pts, &nsplit);
+    double *scratch = nullptr;
+    if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * nsplit * n, (void **)&scratch));
+    CU(vb_launch_predict(de, dn, n, dfe, dfn, df, m, mindist, g_opt.predict_exact, pts, nsplit, scratch, ob.dev, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vb200_predict_2d(const double *east, const double *north, int64_t n,
+                     const double *force_east, const double *force_north, const double *forces,
+                     int64_t m, double mindist, double poisson, double *vec_east,
+                     double *vec_north)
+{
+    if (n < 0 || m < 0) return fail(VB200_E_BADARG, "negative size");
+    if (n == 0) return 0;
+    if (!east || !north || !vec_east || !vec_north || (m > 0 && (!force_east || !force_north || !forces)))
+        return fail(VB200_E_BADARG, "null pointer");
+    if (m > 0x3fffffffLL) return fail(VB200_E_BADARG, "too many forces");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dfe, *dfn, *df;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("in_fe", force_east, m, &dfe, st));
+    CU(stage_in("in_fn", force_north, m, &dfn, st));
+    CU(stage_in("in_f", forces, 2 * m, &df, st));
+    OutBuf oe, on;
+    CU(stage_out("out_pred", vec_east, n, &oe));
+    CU(stage_out("out_pred2", vec_north, n, &on));
+    int pts, nsplit;
+    vb_predict_plan(n, m, &pts, &nsplit);
+    double *scratch = nullptr;
+    if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * 2 * nsplit * n, (void **)&scratch));
+    CU(vb_launch_predict2d(de, dn, n, dfe, dfn, df, m, mindist, poisson, g_opt.predict_exact, pts, nsplit,
+                           scratch, oe.dev, on.dev, st));
+    CU(finish_out(oe, st));
+    CU(finish_out(on, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int64_t vb200_gram_doubles(int64_t cols)
+{
+    const int64_t T = (cols + VB_TILE - 1) / VB_TILE;
+    return T * (T + 1) / 2 * VB_TILE_ELEMS;
+}
+
+int64_t vb200_stats_doubles(int64_t cols)
+{
+    const int64_t T = (cols + VB_TILE - 1) / VB_TILE;
+    return 4 * T * VB_TILE;
+}
+
+static int gram_accumulate_impl(int kind, const double *jac, const double *east, const double *north,
+                                const double *data, const double *weights, int64_t n,
+                                const double *force_east, const double *force_north, int64_t m,
+                                double mindist, double poisson, double *gram_dev, double *stats_dev,
+                                int accumulate, vb200_fit_info *info)
+{
+    if (n < 0 || m <= 0) return fail(VB200_E_BADARG, "bad sizes n=%lld m=%lld", (long long)n, (long long)m);
+    if (!gram_dev || !stats_dev) return fail(VB200_E_BADARG, "null gram/stats buffer");
+    if (!is_device_ptr(gram_dev) || !is_device_ptr(stats_dev))
+        return fail(VB200_E_BADARG, "gram/stats buffers must be device memory");
+    if (n > 0 && (!data || (kind != 2 && (!east || !north)))) return fail(VB200_E_BADARG, "null data pointer");
+    if (kind != 2 && (!force_east || !force_north)) return fail(VB200_E_BADARG, "null force coordinates");
+    cudaStream_t st = 0;
+    VbGramProblem pb = {};
+    pb.kind = kind;
+    pb.n = n;
+    pb.m = m;
+    pb.mindist = mindist;
+    pb.poisson = poisson;
+    const long long rows = vb_sys_rows(pb), cols = vb_sys_cols(pb);
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    if (kind == 2) {
+        CU(stage_in("in_jac", jac, rows * cols, &pb.jac, st));
+    } else {
+        CU(stage_in("in_e", east, n, &pb.east, st));
+        CU(stage_in("in_n", north, n, &pb.north, st));
+        CU(stage_in("in_fe", force_east, m, &pb.fe, st));
+        CU(stage_in("in_fn", force_north, m, &pb.fn, st));
+    }
+    CU(stage_in("in_d", data, rows, &pb.data, st));
+    CU(stage_in("in_w", weights, rows, &pb.weights, st));
+
+    if (info) {
+        info->block_rows = T;
+        info->rows = rows;
+        info->cols = cols;
+    }
+    Span whole;
+    CU(span_begin(&whole, st));
+    prof_reset();
+    if (!accumulate) CU(cudaMemsetAsync(stats_dev, 0, sizeof(double) * 4 * Mpad, st));
+    const long long chunks = (rows + VB_TILE - 1) / VB_TILE;
+    if (chunks == 0 && !accumulate)
+        CU(cudaMemsetAsync(gram_dev, 0, sizeof(double) * vb200_gram_doubles(cols), st));
+    const int slab = g_opt.gram_slab_chunks;
+    double *panel = nullptr;
+    if (chunks > 0)
+        CU(ws_get("panel", sizeof(double) * (size_t)(chunks < slab ? chunks : slab) * T * VB_TILE_ELEMS, (void **)&panel));
+    const long long launches0 = vb_launch_counter;
+    for (long long c0 = 0; c0 < chunks; c0 += slab) {
+        const int nch = (int)((chunks - c0 < slab) ? (chunks - c0) : slab);
+        CU(vb_launch_gram_panel(pb, c0 * VB_TILE, nch, T, panel, stats_dev, st));
+        VbGemmParams g = {};
+        g.a_base = g.b_base = panel;
+        for (int kk = 0; kk < nch; ++kk) g.a_chunk_off[kk] = g.b_chunk_off[kk] = (long long)kk * T * VB_TILE_ELEMS;
+        g.nk = nch;
+        g.c_base = gram_dev;
+        g.T = T;
+        g.j_lo = 0;
+        g.j_hi = T;
+        g.alpha = 1.0;
+        g.accumulate = (accumulate || c0 > 0) ? 1 : 0;
+        CU(timed_gemm(g, st));
+    }
+    CU(cudaEventRecord(whole.b, st));
+    CU(cudaStreamSynchronize(st));
+    if (info) {
+        info->gram_ms += span_ms(whole);
+        info->kernel_launches += vb_launch_counter - launches0;
+    } else {
+        span_ms(whole);
+    }
+    prof_collect(info);
+    return 0;
+}
+
+int vb200_gram_accumulate(int kind, const double *east, const double *north, const double *data,
+                          const double *weights, int64_t n, const double *force_east,
+                          const double *force_north, int64_t m, double mindist, double poisson,
+                          double *gram_dev, double *stats_dev, int accumulate,
+                          vb200_fit_info *info)
+{
+    if (kind != 0 && kind != 1) return fail(VB200_E_BADARG, "kind must be 0 (scalar) or 1 (elastic 2-D)");
+    return gram_accumulate_impl(kind, nullptr, east, north, data, weights, n, force_east, force_north, m,
+                                mindist, poisson, gram_dev, stats_dev, accumulate, info);
+}
+
+int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
+                     double damping, int keep_gram, double *out_params, vb200_fit_info *info)
+{
+    if (cols <= 0 || total_rows <= 0) return fail(VB200_E_BADARG, "bad sizes");
+    if (!gram_dev || !stats_dev || !out_params) return fail(VB200_E_BADARG, "null pointer");
+    if (!(damping > 0.0)) return fail(VB200_E_BADARG, "damping must be > 0 (the damping=None branch of the reference is out of scope)");
+    if (!is_device_ptr(gram_dev) || !is_device_ptr(stats_dev))
+        return fail(VB200_E_BADARG, "gram/stats buffers must be device memory");
+    cudaStream_t st = 0;
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    double *inv_scale, *rhs, *mm;
+    int *d_info;
+    CU(ws_get("inv_scale", sizeof(double) * Mpad, (void **)&inv_scale));
+    CU(ws_get("rhs", sizeof(double) * Mpad, (void **)&rhs));
+    CU(ws_get("minmax", sizeof(double) * 2, (void **)&mm));
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    double *L = gram_dev;
+    if (keep_gram) {
+        CU(ws_get("chol", sizeof(double) * vb200_gram_doubles(cols), (void **)&L));
+        CU(cudaMemcpyAsync(L, gram_dev, sizeof(double) * vb200_gram_doubles(cols), cudaMemcpyDeviceToDevice, st));
+    }
+    OutBuf ob;
+    CU(stage_out("out_params", out_params, cols, &ob));
+    if (info) {
+        info->block_rows = T;
+        info->cols = cols;
+        if (info->rows == 0) info->rows = total_rows;
+    }
+    prof_reset();
+    const long long launches0 = vb_launch_counter;
+    Span fac, sol;
+    CU(span_begin(&fac, st));
+    CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale, rhs, st));
+    CU(vb_launch_scale_system(L, T, cols, inv_scale, damping, st));
+    CU(vb_cholesky_tiled(L, T, g_opt.chol_panel_tiles, d_info, st));
+    CU(cudaEventRecord(fac.b, st));
+    CU(span_begin(&sol, st));
+    CU(vb_solve_tiled(L, T, rhs, st));
+    vb_unscale_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(rhs, inv_scale, cols, ob.dev);
+    vb_diag_minmax_kernel<<<1, 256, 0, st>>>(L, T, cols, mm);
+    vb_launch_counter += 2;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(sol.b, st));
+    CU(finish_out(ob, st));
+    int h_info = 0;
+    double h_mm[2] = {0, 0};
+    CU(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double fms = span_ms(fac), sms = span_ms(sol);
+    if (info) {
+        info->factor_ms += fms;
+        info->solve_ms += sms;
+        info->info = h_info;
+        info->diag_min = h_mm[0];
+        info->diag_max = h_mm[1];
+        info->kernel_launches += vb_launch_counter - launches0;
+    }
+    prof_collect(info);
+    if (h_info > 0) {
+        fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
+        return h_info;
+    }
+    return 0;
+}
+
+static int fit_impl(int kind, const double *jac, const double *east, const double *north,
+                    const double *data, const double *weights, int64_t n, const double *force_east,
+                    const double *force_north, int64_t m, double mindist, double poisson,
+                    double damping, double *out_force, vb200_fit_info *info)
+{
+    if (info) memset(info, 0, sizeof(*info));
+    if (n <= 0 || m <= 0) return fail(VB200_E_BADARG, "bad sizes n=%lld m=%lld", (long long)n, (long long)m);
+    if (!(damping > 0.0)) return fail(VB200_E_BADARG, "damping must be > 0 (the damping=None branch of the reference is out of scope)");
+    const int64_t cols = kind == 1 ? 2 * m : m;
+    const int64_t rows = kind == 1 ? 2 * n : n;
+    double *G, *stats;
+    CU(ws_get("gram", sizeof(double) * vb200_gram_doubles(cols), (void **)&G));
+    CU(ws_get("stats", sizeof(double) * vb200_stats_doubles(cols), (void **)&stats));
+    int rc = gram_accumulate_impl(kind, jac, east, north, data, weights, n, force_east, force_north, m,
+                                  mindist, poisson, G, stats, 0, info);
+    if (rc != 0) return rc;
+    return vb200_gram_solve(G, stats, cols, rows, damping, 0, out_force, info);
+}
+
+int vb200_spline_fit(const double *east, const double *north, const double *data,
+                     const double *weights, int64_t n, const double *force_east,
+                     const double *force_north, int64_t m, double mindist, double damping,
+                     double *out_force, vb200_fit_info *info)
+{
+    return fit_impl(0, nullptr, east, north, data, weights, n, force_east, force_north, m, mindist, 0.0,
+                    damping, out_force, info);
+}
+
+int vb200_spline_fit_2d(const double *east, const double *north, const double *data,
+                        const double *weights, int64_t n, const double *force_east,
+                        const double *force_north, int64_t m, double mindist, double poisson,
+                        double damping, double *out_force, vb200_fit_info *info)
+{
+    return fit_impl(1, nullptr, east, north, data, weights, n, force_east, force_north, m, mindist,
+                    poisson, damping, out_force, info);
+}
+
+int vb200_least_squares(const double *jac, int64_t n, int64_t m, const double *data,
+                        const double *weights, double damping, double *out_params,
+                        vb200_fit_info *info)
+{
+    if (!jac) return fail(VB200_E_BADARG, "null jacobian");
+    return fit_impl(2, jac, nullptr, nullptr, data, weights, n, nullptr, nullptr, m, 0.0, 0.0, damping,
+                    out_params, info);
+}
+
+}  // extern "C"

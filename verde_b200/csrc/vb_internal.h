@@ -1,0 +1,83 @@
+// vb_internal.h -- internal (non-ABI) declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VB_MAX_KCHUNKS 16
+
+// One launch of the DMMA tile kernel:
+//   for every lower-triangle tile (bi, bj), j_lo <= bj < j_hi, bj <= bi < T:
+//     C(bi,bj)[r][c] (+)= alpha * sum_{kk < nk} sum_{k < 128}
+//                          Bop_kk[bi][k][r] * Aop_kk[bj][k][c]
+// where Xop_kk[b] = x_base + x_chunk_off[kk] + b * 16384 is a k-major operand
+// chunk chunk[k][i] of 128 x 128 doubles.
+struct VbGemmParams {
+    const double *a_base;
+    const double *b_base;
+    long long a_chunk_off[VB_MAX_KCHUNKS];
+    long long b_chunk_off[VB_MAX_KCHUNKS];
+    int nk;
+    double *c_base;
+    int T;
+    int j_lo, j_hi;
+    double alpha;
+    int accumulate;  // 0: C = alpha*acc, 1: C += alpha*acc
+};
+
+long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
+cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream);
+// same, but recorded by the API layer's CUDA-event profile (vb_api.cu)
+cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t stream);
+// every kernel launch of the library bumps this (the bench's gpu_launches claim)
+extern long long vb_launch_counter;
+
+cudaError_t vb_init_tables();
+cudaError_t vb_launch_jacobian(const double *e, const double *n, long long npts, const double *fe,
+                               const double *fn, long long m, double mindist, double *jac,
+                               cudaStream_t stream);
+cudaError_t vb_launch_jacobian2d(const double *e, const double *n, long long npts,
+                                 const double *fe, const double *fn, long long m, double mindist,
+                                 double poisson, double *jac, cudaStream_t stream);
+void vb_predict_plan(long long npts, long long m, int *pts, int *nsplit);
+cudaError_t vb_launch_predict(const double *e, const double *n, long long npts, const double *fe,
+                              const double *fn, const double *f, long long m, double mindist,
+                              int exact, int pts, int nsplit, double *scratch, double *out,
+                              cudaStream_t stream);
+cudaError_t vb_launch_predict2d(const double *e, const double *n, long long npts, const double *fe,
+                                const double *fn, const double *f, long long m, double mindist,
+                                double poisson, int exact, int pts, int nsplit, double *scratch,
+                                double *out_e, double *out_n, cudaStream_t stream);
+
+// Gram panel generator (vb_gram.cu)
+//   kind 0: scalar spline     (columns = m forces,   rows = n data)
+//   kind 1: elastic 2-D spline (columns = 2m,         rows = 2n; block structure of
+//           verde/vector.py:461-475)
+//   kind 2: explicit Jacobian  (verde.base.least_squares on a caller-built matrix)
+struct VbGramProblem {
+    int kind;
+    const double *jac;           // kind 2 only: explicit row-major (n, m) Jacobian
+    const double *east, *north;  // n data coordinates
+    const double *data;          // n (kind 0) or 2n (kind 1: east comps then north comps)
+    const double *weights;       // same length as data, or null
+    long long n;                 // data points
+    const double *fe, *fn;       // m force coordinates
+    long long m;                 // forces
+    double mindist, poisson;
+};
+// rows/cols of the least-squares system
+static inline long long vb_sys_rows(const VbGramProblem &p) { return p.kind == 1 ? 2 * p.n : p.n; }
+static inline long long vb_sys_cols(const VbGramProblem &p) { return p.kind == 1 ? 2 * p.m : p.m; }
+
+// Generates rows [row0, row0 + nchunk*128) of sqrt(W) J as k-major chunks into
+// `panel` (layout [chunk][T][128][128]) and ADDS this slab's contribution to
+// stats[0..3][Mpad] = {J^T W d, J^T 1, diag(J^T J), unused}.
+cudaError_t vb_launch_column_scale(const double *stats, int T, long long cols, long long nrows,
+                                   double *inv_scale, double *rhs, cudaStream_t stream);
+cudaError_t vb_launch_scale_system(double *G, int T, long long cols, const double *inv_scale,
+                                   double damping, cudaStream_t stream);
+cudaError_t vb_launch_gram_panel(const VbGramProblem &prob, long long row0, int nchunk, int T,
+                                 double *panel, double *stats, cudaStream_t stream);
+
+// Cholesky and solves on tile-packed storage (vb_chol.cu)
+cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream);
+cudaError_t vb_solve_tiled(const double *L, int T, double *x, cudaStream_t stream);

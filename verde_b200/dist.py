@@ -1,0 +1,120 @@
+"""
+Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink / NVSwitch) for the only exchange the path has.
+
+What shards and how:
+
+* fit       -- data rows are split into contiguous ranges, one per rank; each rank
+               accumulates the partial normal equations of ITS rows (G, J^T W d and
+               the column statistics are all plain sums over rows); ONE all-reduce
+               (sum, float64) of the packed lower triangle + the 4*M statistics
+               vector follows; the m x m Cholesky then runs replicated on every rank
+               (it is the serial part: Amdahl).
+* predict   -- the raveled prediction points are split into contiguous ranges; no
+               communication during compute, one all-gather of the results.
+* SplineCV  -- independent (fold, mindist) Gram jobs are dealt round-robin to ranks;
+               one all-reduce of the (zero-filled) score table at the end.
+
+With a single process (or ``torch.distributed`` not initialised) every helper
+degenerates to the local computation.  The helpers that only do index
+arithmetic or collectives on small tensors also run on the ``gloo`` backend,
+which is how tests/test_dist_cpu.py covers the N > 1 logic without a GPU.
+"""
+import numpy as np
+
+_SHARDING = "auto"
+
+
+def set_sharding(mode):
+    """``"auto"`` (shard when torch.distributed has world_size > 1), ``True`` or ``False``."""
+    global _SHARDING
+    if mode not in ("auto", True, False):
+        raise ValueError("sharding mode must be 'auto', True or False")
+    _SHARDING = mode
+
+
+def world():
+    "(rank, world_size) of the default process group, or (0, 1)."
+    try:
+        import torch.distributed as td
+    except ImportError:  # pragma: no cover
+        return 0, 1
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1
+
+
+def sharding_active():
+    if _SHARDING is False:
+        return False
+    return world()[1] > 1
+
+
+def shard_bounds(total, rank=None, size=None):
+    "Contiguous, balanced [start, stop) of *total* items for *rank* of *size*."
+    if rank is None or size is None:
+        rank, size = world()
+    base, extra = divmod(int(total), int(size))
+    start = rank * base + min(rank, extra)
+    stop = start + base + (1 if rank < extra else 0)
+    return start, stop
+
+
+def round_robin(njobs, rank=None, size=None):
+    "Indices of the jobs this rank owns when jobs are dealt round-robin."
+    if rank is None or size is None:
+        rank, size = world()
+    return list(range(rank, int(njobs), size))
+
+
+def allreduce_sum_(tensor):
+    "In-place sum over ranks of a torch tensor (NCCL for CUDA tensors, gloo for CPU)."
+    import torch.distributed as td
+
+    if world()[1] > 1:
+        td.all_reduce(tensor, op=td.ReduceOp.SUM)
+    return tensor
+
+
+def allreduce_sum_numpy(array):
+    "Sum a small host array over ranks (used for score tables)."
+    import torch
+
+    rank, size = world()
+    if size == 1:
+        return array
+    import torch.distributed as td
+
+    t = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64).copy())
+    if td.get_backend() == "nccl":
+        t = t.cuda()
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t.cpu().numpy().reshape(np.shape(array))
+
+
+def allgather_concat(local, total):
+    """
+    Concatenate each rank's contiguous slice (``shard_bounds`` order) of a 1-D
+    float64 result of global length *total*; every rank gets the full array.
+    """
+    import torch
+
+    rank, size = world()
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if size == 1:
+        return local
+    import torch.distributed as td
+
+    nccl = td.get_backend() == "nccl"
+    longest = max(shard_bounds(total, r, size)[1] - shard_bounds(total, r, size)[0] for r in range(size))
+    buf = torch.zeros(longest, dtype=torch.float64)
+    buf[: local.size] = torch.from_numpy(local)
+    if nccl:
+        buf = buf.cuda()
+    parts = [torch.empty_like(buf) for _ in range(size)]
+    td.all_gather(parts, buf)
+    out = np.empty(int(total), dtype=np.float64)
+    for r, part in enumerate(parts):
+        a, b = shard_bounds(total, r, size)
+        out[a:b] = part[: b - a].cpu().numpy()
+    return out

@@ -1,0 +1,269 @@
+"""
+Host-side mirror of the reference's inner numeric functions.
+
+Same argument order and caller-allocates-output convention as the numba
+functions they replace, so the estimator classes read like the reference's:
+
+===========================  ==================================================
+here                         reference
+===========================  ==================================================
+jacobian_b200                verde/spline.py:642-650  jacobian_numba
+predict_b200                 verde/spline.py:629-639  predict_numba
+jacobian_2d_b200             verde/vector.py:461-475  jacobian_2d_numba
+predict_2d_b200              verde/vector.py:443-458  predict_2d_numba
+least_squares                verde/base/least_squares.py:17-71
+fit_spline / fit_spline_2d   verde/spline.py:462-463 / verde/vector.py:287-288
+                             (Jacobian build + least_squares fused on the GPU;
+                             the Jacobian never exists in memory)
+===========================  ==================================================
+
+Everything executes in ``libverde_b200.so`` on the current CUDA device.
+"""
+import ctypes
+from warnings import warn
+
+import numpy as np
+
+from . import _cabi
+
+LAST_FIT_INFO = {}
+
+
+def _remember(info):
+    LAST_FIT_INFO.clear()
+    LAST_FIT_INFO.update(info.as_dict())
+
+
+def jacobian_b200(east, north, force_east, force_north, mindist, jac):
+    "Fill the (n, m) row-major float64 array *jac* with the spline Green's functions."
+    lib = _cabi.require_device()
+    e, n, fe, fn = (_cabi.f64(a) for a in (east, north, force_east, force_north))
+    if jac.dtype != np.float64 or not jac.flags.c_contiguous:
+        out = np.empty((e.size, fe.size), dtype=np.float64)
+    else:
+        out = jac
+    _cabi.check(lib.vb200_jacobian(_cabi.ptr(e), _cabi.ptr(n), e.size, _cabi.ptr(fe), _cabi.ptr(fn),
+                                   fe.size, float(mindist), _cabi.ptr(out)), "jacobian")
+    if out is not jac:
+        jac[:] = out
+    return jac
+
+
+def predict_b200(east, north, force_east, force_north, mindist, forces, result):
+    "result[i] = sum_j g(east[i]-force_east[j], north[i]-force_north[j]) * forces[j]"
+    lib = _cabi.require_device()
+    e, n, fe, fn, f = (_cabi.f64(a) for a in (east, north, force_east, force_north, forces))
+    direct = result.dtype == np.float64 and result.flags.c_contiguous
+    out = result if direct else np.empty(e.size, dtype=np.float64)
+    _cabi.check(lib.vb200_predict(_cabi.ptr(e), _cabi.ptr(n), e.size, _cabi.ptr(fe), _cabi.ptr(fn),
+                                  _cabi.ptr(f), f.size, float(mindist), _cabi.ptr(out)), "predict")
+    if not direct:
+        result[:] = out
+    return result
+
+
+def jacobian_2d_b200(east, north, force_east, force_north, mindist, poisson, jac):
+    "Fill the (2n, 2m) block Jacobian [[ee, ne], [ne, nn]] of the elastic spline."
+    lib = _cabi.require_device()
+    e, n, fe, fn = (_cabi.f64(a) for a in (east, north, force_east, force_north))
+    direct = jac.dtype == np.float64 and jac.flags.c_contiguous
+    out = jac if direct else np.empty((2 * e.size, 2 * fe.size), dtype=np.float64)
+    _cabi.check(lib.vb200_jacobian_2d(_cabi.ptr(e), _cabi.ptr(n), e.size, _cabi.ptr(fe), _cabi.ptr(fn),
+                                      fe.size, float(mindist), float(poisson), _cabi.ptr(out)), "jacobian_2d")
+    if not direct:
+        jac[:] = out
+    return jac
+
+
+def predict_2d_b200(east, north, force_east, force_north, mindist, poisson, forces, vec_east, vec_north):
+    "Coupled 2-component prediction; *forces* = east forces then north forces."
+    lib = _cabi.require_device()
+    e, n, fe, fn, f = (_cabi.f64(a) for a in (east, north, force_east, force_north, forces))
+    if f.size != 2 * fe.size:
+        raise ValueError("forces must have 2 * n_forces elements ({} given for {} forces)".format(f.size, fe.size))
+    direct = all(a.dtype == np.float64 and a.flags.c_contiguous for a in (vec_east, vec_north))
+    oe = vec_east if direct else np.empty(e.size, dtype=np.float64)
+    on = vec_north if direct else np.empty(e.size, dtype=np.float64)
+    _cabi.check(lib.vb200_predict_2d(_cabi.ptr(e), _cabi.ptr(n), e.size, _cabi.ptr(fe), _cabi.ptr(fn),
+                                     _cabi.ptr(f), fe.size, float(mindist), float(poisson),
+                                     _cabi.ptr(oe), _cabi.ptr(on)), "predict_2d")
+    if not direct:
+        vec_east[:] = oe
+        vec_north[:] = on
+    return vec_east, vec_north
+
+
+def _require_damping(damping):
+    if damping is None:
+        raise NotImplementedError(
+            "damping=None (un-regularised least squares) is outside the B200 hot path: the "
+            "reference solves it with a scikit-learn-version-dependent truncated SVD "
+            "(sklearn LinearRegression -> scipy.linalg.lstsq(cond=...)); see DESIGN.md. "
+            "Pass a positive damping."
+        )
+    if not damping > 0:
+        raise ValueError("damping must be positive, got {!r}".format(damping))
+
+
+def _warn_underdetermined(ndata, nparams):
+    # verde/base/least_squares.py:57-62 (same text)
+    if ndata < nparams:
+        warn("Under-determined problem detected (ndata, nparams)={}.".format((ndata, nparams)))
+
+
+def least_squares(jacobian, data, weights, damping=None, copy_jacobian=False):  # noqa: U100
+    """
+    Damped weighted least squares on an explicit Jacobian, on the GPU.
+
+    Same algebra as the reference (column scaling by the population standard
+    deviation, ``(Js^T W Js + damping I) c = Js^T W d``, parameters unscaled on
+    return).  The Jacobian is never modified, so *copy_jacobian* is accepted for
+    signature compatibility only.
+    """
+    lib = _cabi.require_device()
+    jacobian = np.ascontiguousarray(jacobian, dtype=np.float64)
+    if jacobian.ndim != 2:
+        raise ValueError("jacobian must be 2-D")
+    _warn_underdetermined(*jacobian.shape)
+    _require_damping(damping)
+    d = _cabi.f64(data)
+    if d.size != jacobian.shape[0]:
+        raise ValueError("data size {} does not match the Jacobian rows {}".format(d.size, jacobian.shape[0]))
+    w = None if weights is None else _cabi.f64(weights)
+    params = np.empty(jacobian.shape[1], dtype=np.float64)
+    info = _cabi.FitInfo()
+    rc = lib.vb200_least_squares(_cabi.ptr(jacobian), jacobian.shape[0], jacobian.shape[1], _cabi.ptr(d),
+                                 _cabi.ptr(w), float(damping), _cabi.ptr(params), ctypes.byref(info))
+    _remember(info)
+    _cabi.check(rc, "least_squares")
+    return params
+
+
+def fit_spline(east, north, data, weights, force_east, force_north, mindist, damping):
+    "Forces of the scalar spline; Jacobian build, Gram, Cholesky and solve all on the GPU."
+    lib = _cabi.require_device()
+    e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
+    _warn_underdetermined(e.size, fe.size)
+    _require_damping(damping)
+    w = None if weights is None else _cabi.f64(weights)
+    force = np.empty(fe.size, dtype=np.float64)
+    info = _cabi.FitInfo()
+    rc = lib.vb200_spline_fit(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+                              _cabi.ptr(fn), fe.size, float(mindist), float(damping), _cabi.ptr(force),
+                              ctypes.byref(info))
+    _remember(info)
+    _cabi.check(rc, "Spline.fit")
+    return force
+
+
+def fit_spline_2d(east, north, data, weights, force_east, force_north, mindist, poisson, damping):
+    "Forces (east then north) of the 2-D elastic spline; *data*/*weights* stacked east-then-north."
+    lib = _cabi.require_device()
+    e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
+    _warn_underdetermined(2 * e.size, 2 * fe.size)
+    _require_damping(damping)
+    w = None if weights is None else _cabi.f64(weights)
+    force = np.empty(2 * fe.size, dtype=np.float64)
+    info = _cabi.FitInfo()
+    rc = lib.vb200_spline_fit_2d(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+                                 _cabi.ptr(fn), fe.size, float(mindist), float(poisson), float(damping),
+                                 _cabi.ptr(force), ctypes.byref(info))
+    _remember(info)
+    _cabi.check(rc, "VectorSpline2D.fit")
+    return force
+
+
+class GramSystem:
+    """
+    Staged fit on device-resident normal equations (C ABI ``vb200_gram_*``).
+
+    Holds G = J^T W J (tile-packed lower triangle) and the statistics vector in
+    HBM as torch CUDA tensors so that (a) ranks can all-reduce them over NCCL
+    between ``accumulate`` and ``solve`` and (b) SplineCV can re-solve one Gram
+    matrix for many dampings (``keep=True``).
+    """
+
+    def __init__(self, cols):
+        import torch
+
+        self._lib = _cabi.require_device()
+        self.cols = int(cols)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.gram = torch.empty(self._lib.vb200_gram_doubles(self.cols), dtype=torch.float64, device=dev)
+        self.stats = torch.empty(self._lib.vb200_stats_doubles(self.cols), dtype=torch.float64, device=dev)
+        self.info = _cabi.FitInfo()
+        self._torch = torch
+
+    def accumulate(self, kind, east, north, data, weights, force_east, force_north, mindist,
+                   poisson=0.0, accumulate=False):
+        e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
+        w = None if weights is None else _cabi.f64(weights)
+        self._torch.cuda.synchronize()
+        rc = self._lib.vb200_gram_accumulate(
+            int(kind), _cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+            _cabi.ptr(fn), fe.size, float(mindist), float(poisson), _cabi.ptr(self.gram),
+            _cabi.ptr(self.stats), int(bool(accumulate)), ctypes.byref(self.info))
+        _cabi.check(rc, "gram_accumulate")
+        return self
+
+    def allreduce(self):
+        "Sum the partial normal equations over ranks (NCCL all-reduce over NVLink)."
+        from . import dist
+
+        dist.allreduce_sum_(self.gram)
+        dist.allreduce_sum_(self.stats)
+        self._torch.cuda.synchronize()
+        return self
+
+    def solve(self, total_rows, damping, keep=False):
+        _require_damping(damping)
+        params = np.empty(self.cols, dtype=np.float64)
+        self._torch.cuda.synchronize()
+        rc = self._lib.vb200_gram_solve(_cabi.ptr(self.gram), _cabi.ptr(self.stats), self.cols,
+                                        int(total_rows), float(damping), int(bool(keep)),
+                                        _cabi.ptr(params), ctypes.byref(self.info))
+        _remember(self.info)
+        _cabi.check(rc, "gram_solve")
+        return params
+
+
+def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindist, poisson, damping):
+    """
+    Row-sharded fit: every rank holds the full inputs, builds the normal
+    equations of its contiguous row range, one all-reduce, replicated solve.
+    *data*/*weights* are per-component tuples for kind 1, plain arrays for kind 0.
+    """
+    from . import dist
+
+    e, n, fe, fn = (_cabi.f64(a) for a in (east, north, force_east, force_north))
+    a, b = dist.shard_bounds(e.size)
+    if kind == 1:
+        d = np.concatenate([_cabi.f64(c)[a:b] for c in data])
+        w = None if weights is None else np.concatenate([_cabi.f64(c)[a:b] for c in weights])
+        rows, cols = 2 * e.size, 2 * fe.size
+    else:
+        d = _cabi.f64(data)[a:b]
+        w = None if weights is None else _cabi.f64(weights)[a:b]
+        rows, cols = e.size, fe.size
+    _warn_underdetermined(rows, cols)
+    _require_damping(damping)
+    system = GramSystem(cols)
+    system.accumulate(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson)
+    system.allreduce()
+    return system.solve(rows, damping)
+
+
+def predict_sharded(east, north, force_east, force_north, mindist, forces, poisson=None):
+    "Point-sharded predict + all-gather; returns full-length 1-D result(s)."
+    from . import dist
+
+    e, n = _cabi.f64(east), _cabi.f64(north)
+    a, b = dist.shard_bounds(e.size)
+    if poisson is None:
+        local = np.empty(b - a, dtype=np.float64)
+        predict_b200(e[a:b], n[a:b], force_east, force_north, mindist, forces, local)
+        return dist.allgather_concat(local, e.size)
+    le = np.empty(b - a, dtype=np.float64)
+    ln = np.empty(b - a, dtype=np.float64)
+    predict_2d_b200(e[a:b], n[a:b], force_east, force_north, mindist, poisson, forces, le, ln)
+    return dist.allgather_concat(le, e.size), dist.allgather_concat(ln, e.size)
