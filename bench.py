@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the Green's-function spline hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size n]
+
+A STEP is one pass of the hot path over one batch of synthetic CheckerBoard
+input: ``Spline(damping=1e-6, mindist=1e-5).fit`` followed by the grid predict.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+  N = 1   50 000 scattered points, forces at the data (50k x 50k FP64 normal
+          matrix + Cholesky on one B200), grid 2000 x 2000.
+  N > 1   weak scaling of the same step: 50 000 * N data rows (sharded across
+          ranks, one NCCL all-reduce of the Gram matrix), 50 000 forces from a
+          second seeded scatter, grid 2000 x (2000 * N) points sharded across
+          ranks (at N = 8 this is configs[2]'s 400k x 50k system).
+
+Metric: grid points predicted per second of whole-step time (fit + predict),
+whole job.  The JSON line also carries the two quantities BASELINE.json names
+separately (``fit_s``, ``predict_gpts_per_s``) and the FP64 roofline fraction.
+
+value  -- inputs resident in HBM (device pointers through the C ABI).
+e2e    -- the estimator API (``Spline.fit`` / ``Spline.predict``) with pinned HOST
+          arrays: H2D of the inputs and D2H of forces and grid inside the timing.
+Timing -- CUDA events on the launching (legacy default) stream, barrier +
+          synchronize on both sides, max over ranks.  Inputs are far larger than
+          L2 (10 GB Gram matrix, 400+ MB panels), so no explicit L2 flush is used.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spline_fit_plus_grid_predict_points_per_s@50k_forces"
+UNIT = "Mpts/s"
+DAMPING, MINDIST = 1e-6, 1e-5
+REGION = (0, 5000, -5000, 0)
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic workload (CheckerBoard defaults of verde/synthetic.py:65-118, scatter of
+# verde/coordinates.py:183-186: easting then northing from RandomState(seed).uniform)
+# ---------------------------------------------------------------------------------------
+def make_workload(n_data, n_forces, grid_shape, forces_at_data):
+    rng = np.random.RandomState(0)
+    east = rng.uniform(REGION[0], REGION[1], n_data)
+    north = rng.uniform(REGION[2], REGION[3], n_data)
+    data = 1000.0 * np.sin((2 * np.pi / 2500.0) * east) * np.cos((2 * np.pi / 2500.0) * north)
+    if forces_at_data:
+        fe, fn = east, north
+    else:
+        rng1 = np.random.RandomState(1)
+        fe = rng1.uniform(REGION[0], REGION[1], n_forces)
+        fn = rng1.uniform(REGION[2], REGION[3], n_forces)
+    ge = np.linspace(east.min(), east.max(), grid_shape[1])
+    gn = np.linspace(north.min(), north.max(), grid_shape[0])
+    return east, north, data, fe, fn, ge, gn
+
+
+class ClockSampler:
+    "nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                mx.append(float(row[1]))
+                power.append(float(row[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, cell in zip(names, row[3:7]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "power_w_max": max(power) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the oracle (numpy/C restatement of the reference) on a bounded sample
+# ---------------------------------------------------------------------------------------
+def cpu_reference_step(sample_n, sample_grid, full):
+    """
+    Time the reference's CPU algorithm (oracle/ restatement: OpenMP Green's kernels +
+    numpy/scipy normal equations, the same BLAS/LAPACK calls sklearn makes) on a
+    bounded sample and extrapolate to the full workload with the cost model of
+    SURVEY.md 8d: Jacobian ~ n*m, scaler ~ n*m, Gram ~ n*m^2, Cholesky ~ m^3/3,
+    predict ~ N*M.
+    """
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import scipy.linalg
+    import verde_oracle as vo
+
+    east, north, data, _, _, _, _ = make_workload(sample_n, sample_n, (8, 8), True)
+    t0 = time.perf_counter()
+    jac = vo.jacobian(east, north, east, north, MINDIST)
+    t_jac = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    scale = vo.column_scale(jac)
+    jac /= scale
+    t_scale = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    gram = jac.T @ jac
+    rhs = jac.T @ data
+    t_gram = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    gram.flat[:: sample_n + 1] += DAMPING
+    coef = scipy.linalg.solve(gram, rhs, assume_a="pos", overwrite_a=True) / scale
+    t_solve = time.perf_counter() - t0
+    ge = np.linspace(east.min(), east.max(), sample_grid)
+    gn = np.linspace(north.min(), north.max(), sample_grid)
+    gx, gy = np.meshgrid(ge, gn)
+    t0 = time.perf_counter()
+    vo.predict(gx, gy, east, north, MINDIST, coef)
+    t_pred = time.perf_counter() - t0
+
+    n, m, npts = full
+    s = float(sample_n)
+    fit_full = (t_jac + t_scale) * (n * m) / (s * s) + t_gram * (n * m * m) / s**3 + t_solve * (m / s) ** 3
+    pred_rate = sample_grid * sample_grid * s / t_pred  # pair evaluations / s
+    pred_full = npts * m / pred_rate
+    return {
+        "sample_seconds": t_jac + t_scale + t_gram + t_solve + t_pred,
+        "fit_s_extrapolated": fit_full,
+        "predict_s_extrapolated": pred_full,
+        "predict_gpairs_per_s": pred_rate * 1e-9,
+        "value": npts / (fit_full + pred_full) * 1e-6,
+        "phases_s": {"jacobian": t_jac, "scaler": t_scale, "gram": t_gram, "solve": t_solve, "predict": t_pred},
+    }
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n = 50_000 * world
+    m = 50_000
+    npts = 2000 * 2000 * world
+    cores = os.cpu_count() or 1
+    sample_n, sample_grid = args.cpu_sample, 150
+    for _ in range(args.warmup):
+        cpu_reference_step(min(1500, sample_n), 40, (n, m, npts))
+    times, last = [], None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference_step(sample_n, sample_grid, (n, m, npts))
+        times.append(time.perf_counter() - t0)
+    sample = ("oracle (C/OpenMP Green's kernels + numpy/scipy BLAS/LAPACK normal equations) on n=m={} "
+              "points and a {}x{} grid; extrapolated to n={}, m={}, {} grid points with n*m, n*m^2, "
+              "m^3/3 and N*M scaling").format(sample_n, sample_grid, sample_grid, n, m, npts)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": last["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (last["fit_s_extrapolated"] + last["predict_s_extrapolated"]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "fit_s": last["fit_s_extrapolated"], "predict_gpts_per_s": npts / last["predict_s_extrapolated"] * 1e-9,
+        "cpu_baseline": {"value": last["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "sample_wall_s": statistics.mean(times), "phases_s": last["phases_s"],
+                         "extrapolated": True},
+        "e2e": {"value": last["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {
+        "workload": ("BASELINE configs[1]: Spline(damping=1e-6, mindist=1e-5), CheckerBoard scatter of 50k points, "
+                     "forces at data, grid 2000x2000" if world == 1 else
+                     "weak-scaled configs[1] (= configs[2] at N=8): {} data rows sharded over {} ranks, 50k forces, "
+                     "grid 2000x{} sharded".format(50_000 * world, world, 2000 * world)),
+        "n_data": 50_000 * world, "n_forces": 50_000, "grid_points": 2000 * 2000 * world,
+        "damping": DAMPING, "mindist": MINDIST, "parallelism": "rows+grid sharded x{}".format(world),
+        "l2": "inputs larger than L2 (10 GB Gram matrix streamed); no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=50_000, help="data points per rank (default: the BASELINE 50k)")
+    ap.add_argument("--grid", type=int, default=2000, help="grid is GRID x GRID per rank")
+    ap.add_argument("--cpu-sample", type=int, default=8000, help="n=m of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as td
+
+    import verde_b200 as vb
+    from verde_b200 import _cabi, kernels
+
+    torch.cuda.set_device(local_rank)
+    lib = _cabi.require_device()
+    lib.vb200_set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_rank, m = args.size, args.size if world == 1 else min(50_000, args.size)
+    n_total = n_rank * world
+    grid_shape = (args.grid, args.grid * world)
+    npts_total = grid_shape[0] * grid_shape[1]
+    east, north, data, fe, fn, ge, gn = make_workload(n_total, m, grid_shape, forces_at_data=(world == 1))
+    gx, gy = np.meshgrid(ge, gn)
+    gx, gy = gx.ravel(), gy.ravel()
+    a, b = vb.dist.shard_bounds(n_total, rank, world)
+    pa, pb = vb.dist.shard_bounds(npts_total, rank, world)
+    dev = torch.device("cuda", local_rank)
+
+    def to_dev(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+    d_e, d_n, d_d = to_dev(east[a:b]), to_dev(north[a:b]), to_dev(data[a:b])
+    d_fe, d_fn = to_dev(fe), to_dev(fn)
+    d_gx, d_gy = to_dev(gx[pa:pb]), to_dev(gy[pa:pb])
+    d_force = torch.empty(m, dtype=torch.float64, device=dev)
+    d_out = torch.empty(pb - pa, dtype=torch.float64, device=dev)
+    system = kernels.GramSystem(m) if world > 1 else None
+    info = _cabi.FitInfo()
+    phase = {}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        "fit + predict with everything resident in HBM (device pointers through the C ABI)"
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        if world == 1:
+            rc = lib.vb200_spline_fit(_cabi.ptr(d_e), _cabi.ptr(d_n), _cabi.ptr(d_d), None, b - a, _cabi.ptr(d_fe),
+                                      _cabi.ptr(d_fn), m, MINDIST, DAMPING, _cabi.ptr(d_force), ctypes.byref(info))
+            _cabi.check(rc, "bench fit")
+        else:
+            ctypes.memset(ctypes.byref(info), 0, ctypes.sizeof(info))
+            rc = lib.vb200_gram_accumulate(0, _cabi.ptr(d_e), _cabi.ptr(d_n), _cabi.ptr(d_d), None, b - a,
+                                           _cabi.ptr(d_fe), _cabi.ptr(d_fn), m, MINDIST, 0.0,
+                                           _cabi.ptr(system.gram), _cabi.ptr(system.stats), 0, ctypes.byref(info))
+            _cabi.check(rc, "bench gram")
+            system.allreduce()
+            rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, DAMPING, 0,
+                                      _cabi.ptr(d_force), ctypes.byref(info))
+            _cabi.check(rc, "bench solve")
+        ev[1].record()
+        rc = lib.vb200_predict(_cabi.ptr(d_gx), _cabi.ptr(d_gy), pb - pa, _cabi.ptr(d_fe), _cabi.ptr(d_fn),
+                               _cabi.ptr(d_force), m, MINDIST, _cabi.ptr(d_out))
+        _cabi.check(rc, "bench predict")
+        ev[2].record()
+        torch.cuda.synchronize()
+        phase["fit_ms"] = ev[0].elapsed_time(ev[1])
+        phase["predict_ms"] = ev[1].elapsed_time(ev[2])
+        phase["info"] = info.as_dict()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(ms, op=td.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm ---------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.vb200_launch_count()
+    fit_ms, pred_ms, gemm_ms, gemm_flops, gemm_launches = [], [], 0.0, 0.0, 0
+
+    def counted_step():
+        nonlocal gemm_ms, gemm_flops, gemm_launches
+        device_step()
+        fit_ms.append(phase["fit_ms"])
+        pred_ms.append(phase["predict_ms"])
+        gemm_ms += phase["info"]["gemm_ms"]
+        gemm_flops += phase["info"]["gemm_flops"]
+        gemm_launches += phase["info"]["gemm_launches"]
+
+    total_ms = timed(counted_step, args.steps)
+    launches = lib.vb200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = npts_total / (ms_per_step * 1e-3) * 1e-6
+
+    # ---- end-to-end arm: estimator API, pinned host arrays ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def pinned(x):
+            t = torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+            return t.numpy()
+
+        h_e, h_n, h_d = pinned(east), pinned(north), pinned(data)
+        h_gx, h_gy = pinned(gx), pinned(gy)
+        force_coords = None if world == 1 else (pinned(fe), pinned(fn))
+        result = {}
+
+        def api_step():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", FutureWarning)
+                spline = vb.Spline(damping=DAMPING, mindist=MINDIST, force_coords=force_coords)
+            spline.fit((h_e, h_n), h_d)
+            result["grid"] = spline.predict((h_gx, h_gy))
+            result["force"] = spline.force_
+
+        for _ in range(max(1, min(args.warmup, 1))):
+            api_step()
+        e2e_steps = max(1, min(args.steps, 2))
+        e2e_ms = timed(api_step, e2e_steps) / e2e_steps
+        h2d = 8 * ((b - a) * 3 + (0 if world == 1 else 2 * m) + 2 * m + 2 * (pb - pa) + m)
+        d2h = 8 * (m + (pb - pa))
+        e2e = {"value": npts_total / (e2e_ms * 1e-3) * 1e-6, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "verde_b200.Spline.fit + Spline.predict (host numpy, pinned)"}
+        # parity spot check of the two arms against each other (same forces, same grid)
+        dev_force = d_force.cpu().numpy()
+        e2e["force_vs_device_arm"] = float(np.max(np.abs(result["force"] - dev_force)) / np.max(np.abs(dev_force)))
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    peak = lib.vb200_measure_fp64_peak_tflops(0)
+    achieved = gemm_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+    fit_s = statistics.mean(fit_ms) * 1e-3
+    pred_s = statistics.mean(pred_ms) * 1e-3
+    n_pairs = (pb - pa) * m
+    algorithmic_fit_flops = (b - a) * m * (m + 1) + m**3 / 3.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+        "fit_s": fit_s, "predict_s": pred_s, "predict_gpts_per_s": (pb - pa) * world / pred_s * 1e-9,
+        "predict_gpairs_per_s": n_pairs / pred_s * 1e-9,
+        "fit_phases_ms": {k: phase["info"][k] for k in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms")},
+        "fit_fp64_frac": algorithmic_fit_flops / fit_s * 1e-12 / peak if peak > 0 else None,
+        "roofline": {
+            "kernel": "vb_gemm_kernel (FP64 DMMA 128x128 tile kernel: Gram accumulation + Cholesky updates)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak > 0 else None, "traffic": None,
+            "peak_source": "FP64 DMMA.8x8x4 issue microbenchmark run in this process "
+                           "(vb200_measure_fp64_peak_tflops; MEASURED_PEAKS.json has no FP64 entry)",
+            "launches_per_step": gemm_launches / args.steps,
+            "algorithmic_flops_per_step": gemm_flops / args.steps,
+            "share_of_step": gemm_ms / total_ms,
+        },
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "diag_min_max": [phase["info"]["diag_min"], phase["info"]["diag_max"]],
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        cpu = cpu_reference_step(args.cpu_sample, 150, (n_total, m, npts_total))
+        line["cpu_baseline"] = {
+            "value": cpu["value"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": ("oracle on n=m={} + 150x150 grid ({:.1f} s of CPU work), extrapolated to the full workload with "
+                       "n*m, n*m^2, m^3/3, N*M scaling").format(args.cpu_sample, cpu["sample_seconds"]),
+            "fit_s_extrapolated": cpu["fit_s_extrapolated"], "predict_gpairs_per_s": cpu["predict_gpairs_per_s"],
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,12 @@ int vb200_set_device(int device);
 int vb200_set_option(const char *key, double value);
 /* frees the cached device workspace (Gram matrix, panels) */
 int vb200_release_workspace(void);
+/* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
+int64_t vb200_launch_count(void);
+/* FP64 issue-rate microbenchmark on the current device, TFLOP/s: kind 0 = DMMA.8x8x4
+ * (mma.sync f64), kind 1 = DFMA.  The roofline denominator of the fit kernels;
+ * returns < 0 on CUDA errors. */
+double vb200_measure_fp64_peak_tflops(int kind);
 
 /* ---- K0: Jacobian materialisation --------------------------------------------------- */
 /* replaces verde/spline.py:642-650 jacobian_numba(east, north, force_east, force_north,

@@ -52,6 +52,8 @@ SIGNATURES = {
     "vb200_set_device": (ctypes.c_int, [ctypes.c_int]),
     "vb200_set_option": (ctypes.c_int, [ctypes.c_char_p, dbl]),
     "vb200_release_workspace": (ctypes.c_int, []),
+    "vb200_launch_count": (i64, []),
+    "vb200_measure_fp64_peak_tflops": (dbl, [ctypes.c_int]),
     "vb200_jacobian": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, ctypes.c_void_p]),
     "vb200_jacobian_2d": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, ctypes.c_void_p]),
     "vb200_predict": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 3 + [i64, dbl, ctypes.c_void_p]),

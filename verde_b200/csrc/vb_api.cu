@@ -227,6 +227,43 @@ __global__ void vb_diag_minmax_kernel(const double *__restrict__ L, int T, long 
     }
 }
 
+// ---- FP64 issue-rate microbenchmark (roofline denominator) -----------------------------
+constexpr int PEAK_ITERS = 2048;
+__global__ void __launch_bounds__(256) vb_peak_dmma_kernel(double *out, double a, double b)
+{
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c[i][0] = threadIdx.x;
+        c[i][1] = i;
+    }
+    for (int it = 0; it < PEAK_ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) vb_peak_dfma_kernel(double *out, double a, double b)
+{
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x + i;
+    for (int it = 0; it < PEAK_ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
 // vb_chol.cu calls the GEMM through this hook so that its launches are timed too.
@@ -270,6 +307,39 @@ int vb200_release_workspace(void)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     g_ws.clear();
     return 0;
+}
+
+int64_t vb200_launch_count(void) { return vb_launch_counter; }
+
+double vb200_measure_fp64_peak_tflops(int kind)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+    const int blocks = sms * 8, threads = 256;
+    double *out = nullptr;
+    if (ws_get("peak", sizeof(double) * blocks * threads, (void **)&out) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0, 0);
+        if (kind == 0) vb_peak_dmma_kernel<<<blocks, threads>>>(out, 1.0000001, 1e-9);
+        else vb_peak_dfma_kernel<<<blocks, threads>>>(out, 1.0000001, 1e-9);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    const double threads_total = (double)blocks * threads;
+    const double flops = kind == 0 ? threads_total / 32 * PEAK_ITERS * 8 * 256 * 2.0
+                                   : threads_total * PEAK_ITERS * 16 * 2.0;
+    return flops / best * 1e-9;
 }
 
 int vb200_jacobian(const double *east, const double *north, int64_t n, const double *force_east,
