@@ -406,7 +406,7 @@ def main():
         "fit_phases_ms": {k: phase["info"][k] for k in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms")},
         "fit_fp64_frac": algorithmic_fit_flops / fit_s * 1e-12 / peak if peak > 0 else None,
         "roofline": {
-            "kernel": "vb_gemm_kernel (FP64 DMMA 128x128 tile kernel: Gram accumulation + Cholesky updates)",
+            "kernel": "vb_gemm_tma_kernel (FP64 DMMA 128x128 tile kernel, TMA-bulk/mbarrier pipeline: Gram accumulation + Cholesky updates)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak > 0 else None, "traffic": None,
             "peak_source": "FP64 DMMA.8x8x4 issue microbenchmark run in this process "

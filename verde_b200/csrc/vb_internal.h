@@ -30,6 +30,8 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream);
 cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t stream);
 // every kernel launch of the library bumps this (the bench's gpu_launches claim)
 extern long long vb_launch_counter;
+// DMMA tile kernel flavour (see vb_gemm.cu)
+extern int vb_gemm_variant;
 
 cudaError_t vb_init_tables();
 cudaError_t vb_launch_jacobian(const double *e, const double *n, long long npts, const double *fe,
