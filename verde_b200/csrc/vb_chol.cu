@@ -21,47 +21,60 @@
 
 namespace {
 
-constexpr int POTRF_THREADS = 256;
-constexpr int POTRF_LD = VB_TILE + 1;
+constexpr int POTRF_THREADS = 128;
+constexpr int POTRF_BLK = 16;
 
-// Factor one diagonal tile in place (lower triangle), column by column.
+// Factor one diagonal tile in place (lower triangle).  Thread r owns row r; the tile
+// lives in shared memory (column-major, so a thread's accesses s[c*128 + r] are
+// conflict-free and L(c0.., k) rows are contiguous for LDS.128 broadcasts).  Left-looking
+// over 16-column blocks held in registers: the block is first updated with all columns to
+// its left (16 independent FMAs per own-row load), then factored column by column with
+// one shared-memory publish + barrier per pivot and per column.
 __global__ void __launch_bounds__(POTRF_THREADS)
 vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info)
 {
-    extern __shared__ double s[];  // s[c * POTRF_LD + r]
-    __shared__ int s_fail;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_fail = 0;
-    for (int idx = tid; idx < VB_TILE_ELEMS; idx += POTRF_THREADS) {
-        const int c = idx >> 7, r = idx & 127;
-        s[c * POTRF_LD + r] = tile[idx];
-    }
+    extern __shared__ __align__(16) double s[];  // s[c * 128 + r]
+    __shared__ double s_piv[POTRF_BLK];
+    const int r = threadIdx.x;
+    for (int idx = r; idx < VB_TILE_ELEMS / 2; idx += POTRF_THREADS)
+        reinterpret_cast<double2 *>(s)[idx] = reinterpret_cast<const double2 *>(tile)[idx];
     __syncthreads();
-    for (int c = 0; c < VB_TILE; ++c) {
-        const double piv = s[c * POTRF_LD + c];
-        if (!(piv > 0.0)) {
-            if (tid == 0) {
-                s_fail = 1;
-                atomicCAS(d_info, 0, k * VB_TILE + c + 1);
+    for (int c0 = 0; c0 < VB_TILE; c0 += POTRF_BLK) {
+        double a[POTRF_BLK];
+#pragma unroll
+        for (int c = 0; c < POTRF_BLK; ++c) a[c] = s[(c0 + c) * VB_TILE + r];
+        for (int kp = 0; kp < c0; ++kp) {
+            const double lrk = s[kp * VB_TILE + r];
+            const double2 *lc = reinterpret_cast<const double2 *>(s + kp * VB_TILE + c0);
+#pragma unroll
+            for (int c2 = 0; c2 < POTRF_BLK / 2; ++c2) {
+                const double2 l = lc[c2];
+                a[2 * c2] = fma(-lrk, l.x, a[2 * c2]);
+                a[2 * c2 + 1] = fma(-lrk, l.y, a[2 * c2 + 1]);
             }
         }
-        const double l = sqrt(piv);
-        const double inv = 1.0 / l;
-        __syncthreads();  // everyone has read the pivot
-        if (tid == 0) s[c * POTRF_LD + c] = l;
-        for (int r = c + 1 + tid; r < VB_TILE; r += POTRF_THREADS) s[c * POTRF_LD + r] *= inv;
-        __syncthreads();
-        // trailing update of columns c+1..127 (lower part): s[c2][r] -= s[c][r]*s[c][c2]
-        const int rem = VB_TILE - 1 - c;
-        for (int idx = tid; idx < rem * rem; idx += POTRF_THREADS) {
-            const int c2 = c + 1 + idx / rem, r = c + 1 + idx % rem;
-            if (r >= c2) s[c2 * POTRF_LD + r] = fma(-s[c * POTRF_LD + r], s[c * POTRF_LD + c2], s[c2 * POTRF_LD + r]);
+#pragma unroll
+        for (int kk = 0; kk < POTRF_BLK; ++kk) {
+            const int cg = c0 + kk;
+            if (r == cg) {
+                const double piv = a[kk];
+                if (!(piv > 0.0)) atomicCAS(d_info, 0, k * VB_TILE + cg + 1);
+                s_piv[kk] = sqrt(piv);
+            }
+            __syncthreads();
+            const double l = s_piv[kk];
+            const double x = (r == cg) ? l : a[kk] / l;
+            a[kk] = x;
+            s[cg * VB_TILE + r] = x;
+            __syncthreads();
+#pragma unroll
+            for (int c = kk + 1; c < POTRF_BLK; ++c) a[c] = fma(-x, s[cg * VB_TILE + c0 + c], a[c]);
         }
-        __syncthreads();
     }
-    for (int idx = tid; idx < VB_TILE_ELEMS; idx += POTRF_THREADS) {
-        const int c = idx >> 7, r = idx & 127;
-        tile[idx] = (r >= c) ? s[c * POTRF_LD + r] : 0.0;
+    __syncthreads();
+    for (int idx = r; idx < VB_TILE_ELEMS; idx += POTRF_THREADS) {
+        const int c = idx >> 7, rr = idx & 127;
+        tile[idx] = (rr >= c) ? s[idx] : 0.0;
     }
 }
 
@@ -121,18 +134,20 @@ vb_trsm_tiles_kernel(double *__restrict__ Lmat, int T, int k)
 __global__ void __launch_bounds__(VB_TILE)
 vb_fwd_diag_kernel(const double *__restrict__ Lmat, int T, int k, double *__restrict__ x)
 {
-    __shared__ double sx[VB_TILE];
+    extern __shared__ __align__(16) double st[];  // st[c * 128 + r] = L_kk(r, c)
+    __shared__ double sy[VB_TILE];
     const double *tile = Lmat + vb_tile_index(k, k, T) * VB_TILE_ELEMS;
     const int r = threadIdx.x;
-    sx[r] = x[k * VB_TILE + r];
+    for (int idx = r; idx < VB_TILE_ELEMS / 2; idx += VB_TILE)
+        reinterpret_cast<double2 *>(st)[idx] = reinterpret_cast<const double2 *>(tile)[idx];
+    double v = x[k * VB_TILE + r];
     __syncthreads();
     for (int c = 0; c < VB_TILE; ++c) {
-        if (r == c) sx[c] = sx[c] / tile[c * VB_TILE + c];
+        if (r == c) sy[c] = v / st[c * VB_TILE + c];
         __syncthreads();
-        if (r > c) sx[r] = fma(-tile[c * VB_TILE + r], sx[c], sx[r]);
-        __syncthreads();
+        if (r > c) v = fma(-st[c * VB_TILE + r], sy[c], v);
     }
-    x[k * VB_TILE + r] = sx[r];
+    x[k * VB_TILE + r] = sy[r];
 }
 
 __global__ void __launch_bounds__(VB_TILE)
@@ -159,17 +174,18 @@ vb_fwd_update_kernel(const double *__restrict__ Lmat, int T, int k, double *__re
 __global__ void __launch_bounds__(VB_TILE)
 vb_bwd_diag_kernel(const double *__restrict__ Lmat, int T, int k, double *__restrict__ x)
 {
+    extern __shared__ __align__(16) double st[];  // st[r * 129 + c] = L_kk(r, c)  (row-major, padded)
     __shared__ double sx[VB_TILE];
     const double *tile = Lmat + vb_tile_index(k, k, T) * VB_TILE_ELEMS;
     const int r = threadIdx.x;
-    sx[r] = x[k * VB_TILE + r];
+    for (int c = 0; c < VB_TILE; ++c) st[r * (VB_TILE + 1) + c] = tile[c * VB_TILE + r];
+    double v = x[k * VB_TILE + r];
     __syncthreads();
     for (int c = VB_TILE - 1; c >= 0; --c) {
-        if (r == c) sx[c] = sx[c] / tile[c * VB_TILE + c];
+        if (r == c) sx[c] = v / st[c * (VB_TILE + 1) + c];
         __syncthreads();
-        // (L^T)(r, c) = L(c, r), r < c: stored at tile[r * 128 + c]
-        if (r < c) sx[r] = fma(-tile[r * VB_TILE + c], sx[c], sx[r]);
-        __syncthreads();
+        // (L^T)(r, c) = L(c, r) for r < c
+        if (r < c) v = fma(-st[c * (VB_TILE + 1) + r], sx[c], v);
     }
     x[k * VB_TILE + r] = sx[r];
 }
@@ -205,7 +221,7 @@ long long col_base(int c, int T)
 cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream)
 {
     cudaError_t err;
-    const int potrf_smem = VB_TILE * POTRF_LD * (int)sizeof(double);
+    const int potrf_smem = VB_TILE_ELEMS * (int)sizeof(double);
     const int trsm_smem = VB_TILE_ELEMS * (int)sizeof(double);
     if ((err = cudaFuncSetAttribute(vb_potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(vb_trsm_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem)) != cudaSuccess) return err;
@@ -258,13 +274,18 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
 // x (length T*128) is overwritten by the solution of L L^T x = b.
 cudaError_t vb_solve_tiled(const double *L, int T, double *x, cudaStream_t stream)
 {
+    const int fwd_smem = VB_TILE_ELEMS * (int)sizeof(double);
+    const int bwd_smem = VB_TILE * (VB_TILE + 1) * (int)sizeof(double);
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(vb_fwd_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(vb_bwd_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem)) != cudaSuccess) return err;
     for (int k = 0; k < T; ++k) {
-        vb_fwd_diag_kernel<<<1, VB_TILE, 0, stream>>>(L, T, k, x);
+        vb_fwd_diag_kernel<<<1, VB_TILE, fwd_smem, stream>>>(L, T, k, x);
         if (k + 1 < T) vb_fwd_update_kernel<<<T - k - 1, VB_TILE, 0, stream>>>(L, T, k, x);
         vb_launch_counter += (k + 1 < T) ? 2 : 1;
     }
     for (int k = T - 1; k >= 0; --k) {
-        vb_bwd_diag_kernel<<<1, VB_TILE, 0, stream>>>(L, T, k, x);
+        vb_bwd_diag_kernel<<<1, VB_TILE, bwd_smem, stream>>>(L, T, k, x);
         if (k > 0) vb_bwd_update_kernel<<<k, 256, 0, stream>>>(L, T, k, x);
         vb_launch_counter += (k > 0) ? 2 : 1;
     }

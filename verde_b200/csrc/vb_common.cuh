@@ -91,17 +91,18 @@ __device__ __forceinline__ void vb_logtab_stage(double *smem_tab, const double2 
 }
 
 // log(d) for normal positive d.  `tab` points at this lane's replica column:
-// reinterpret_cast<const double2*>(smem_tab) + (lane & 7).
+// reinterpret_cast<const double2*>(smem_tab) + (lane & 7).  Never produces inf/NaN:
+// d = 0 reads as 2^-1023 (finite log), so r2 * log(r2) is an exact 0 at r2 = 0.
 __device__ __forceinline__ double vb_log_fast(double d, const double2 *tab)
 {
     const int hi = __double2hiint(d);
     const int lo = __double2loint(d);
-    const int idx = (hi >> 13) & 0x7F;
+    // byte offset of table entry idx = mantissa bits 19..13: idx * 128
+    const int off = (hi >> 6) & 0x3F80;
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
-    // double(e) without an I2F: 2^52 + 2^31 + (e ^ 0x80000000) trick
-    const int e = (hi >> 20) - 1023;
-    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
-    const double2 t = tab[idx * 8];
+    // double(biased exponent - 1023) without an I2F: 2^52 + biased as a bit pattern
+    const double ed = __hiloint2double(0x43300000, (unsigned)hi >> 20) - 4503599627371519.0;
+    const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(tab) + off);
     const double r = fma(m, t.x, -1.0);
     // log1p(r), |r| <= 2^-8: r - r^2/2 + ... + r^7/7
     double q = fma(r, 1.0 / 7.0, -1.0 / 6.0);
@@ -114,49 +115,54 @@ __device__ __forceinline__ double vb_log_fast(double d, const double2 *tab)
     return fma(ed, 0.6931471805599453094, t.y) + l1p;
 }
 
-// sqrt(x) for x >= 0 via rsqrt.approx (MUFU.RSQ64H, 2^-22) + 2 Goldschmidt steps.
+// sqrt(x) for x > 0 (normal): MUFU.RSQ64H seed (rel. error d ~ 2^-22) and ONE third-order
+// correction: with t = x*y, e = 1 - t*y,  sqrt(x) = t (1-e)^(-1/2) = t (1 + e/2 + 3e^2/8) + O(e^3),
+// i.e. relative error ~2.5 d^3 < 2^-60.  5 FP64 issue slots; callers keep x away from 0.
 __device__ __forceinline__ double vb_sqrt_fast(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y;
-    double h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    // x == 0 -> y = inf -> NaN chain; x tiny/denormal is flushed by .ftz likewise
-    return (__double2hiint(x) < 0x00200000) ? 0.0 : g;
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = e * p;
+    return fma(t, q, t);
 }
 
-// d^2 (log d - 1) with d = sqrt(dx^2+dy^2) + mindist.  HAS_MINDIST=false folds the
-// sqrt away: r2 * (0.5*log(r2) - 1).
+// 1/x for normal x: MUFU.RCP64H seed + two Newton steps (4 FP64 issue slots)
+__device__ __forceinline__ double vb_rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// d^2 (log d - 1) with d = sqrt(dx^2+dy^2) + mindist, for FINITE inputs (the predict
+// kernels screen non-finite coordinates / forces outside their inner loop).
+//   HAS_MINDIST = false folds the sqrt away: r2 * (0.5*log(r2) - 1), exactly 0 at r2 = 0
+//   (18 FP64 slots per pair); HAS_MINDIST = true adds 1e-300 to r2 inside the FMA chain so the
+//   rsqrt seed never sees 0 (sqrt -> 1e-150, absorbed by any mindist > 1e-134): 25 slots.
+#define VB_R2_FLOOR 1e-300
 template <bool HAS_MINDIST>
 __device__ __forceinline__ double vb_greens_fast(double dx, double dy, double mindist,
                                                  const double2 *tab)
 {
-    const double r2 = fma(dx, dx, dy * dy);
-    double d, dd, half;
     if (HAS_MINDIST) {
-        d = vb_sqrt_fast(r2) + mindist;
-        dd = d * d;
-        half = 1.0;
+        const double r2 = fma(dx, dx, fma(dy, dy, VB_R2_FLOOR));
+        const double d = vb_sqrt_fast(r2) + mindist;
+        const double lg = vb_log_fast(d, tab);
+        return (d * d) * (lg - 1.0);
     } else {
-        d = r2;
-        dd = r2;
-        half = 0.5;
+        const double r2 = fma(dx, dx, dy * dy);
+        const double lg = vb_log_fast(r2, tab);
+        return r2 * fma(0.5, lg, -1.0);
     }
-    const int hi = __double2hiint(d);
-    const double lg = vb_log_fast(d, tab);
-    double g = dd * fma(half, lg, -1.0);
-    // d < 2^-511 (incl. 0, where the reference gives exactly 0): d^2 underflows anyway
-    if (hi < 0x20000000) g = 0.0;
-    // inf / NaN propagate like the reference's arithmetic would
-    if (hi >= 0x7FF00000) g = d;
-    return g;
 }
 
+// elastic Green's functions (verde/vector.py:393-405) for finite inputs with d > 0
 template <bool HAS_MINDIST>
 __device__ __forceinline__ void vb_greens2d_fast(double dx, double dy, double mindist,
                                                  double three_minus_nu, double one_plus_nu,
@@ -164,17 +170,16 @@ __device__ __forceinline__ void vb_greens2d_fast(double dx, double dy, double mi
                                                  double &g_ne)
 {
     const double dx2 = dx * dx, dy2 = dy * dy;
-    const double r2 = dx2 + dy2;
     double lg, inv_d2;
     if (HAS_MINDIST) {
+        const double r2 = dx2 + (dy2 + VB_R2_FLOOR);
         const double d = vb_sqrt_fast(r2) + mindist;
         lg = vb_log_fast(d, tab);
-        inv_d2 = 1.0 / (d * d);
-        if (__double2hiint(d) >= 0x7FF00000 || __double2hiint(d) < 0x00100000) lg = log(d);
+        inv_d2 = vb_rcp_fast(d * d);
     } else {
+        const double r2 = dx2 + dy2;  // r2 = 0 -> log = -inf, 1/r2 = inf in the reference: screened by caller
         lg = 0.5 * vb_log_fast(r2, tab);
-        inv_d2 = 1.0 / r2;
-        if (__double2hiint(r2) >= 0x7FF00000 || __double2hiint(r2) < 0x00100000) lg = 0.5 * log(r2);
+        inv_d2 = vb_rcp_fast(r2);
     }
     const double ln_r = three_minus_nu * lg;
     const double q = one_plus_nu * inv_d2;

@@ -89,15 +89,22 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
         acc[p] = 0.0;
     }
 
+    // The fast Green's function assumes finite inputs; non-finite forces / force coordinates
+    // poison every output of the CTA, non-finite points poison their own output (NaN, as the
+    // reference's arithmetic would give).
+    int poisoned = 0;
     for (int c0 = m0; c0 < m1; c0 += PRED_CHUNK) {
         const int cn = min(PRED_CHUNK, m1 - c0);
         __syncthreads();
+        int bad = 0;
         for (int t = threadIdx.x; t < cn; t += PRED_THREADS) {
-            s_fe[t] = fe[c0 + t];
-            s_fn[t] = fn[c0 + t];
-            s_f[t] = force[c0 + t];
+            const double a = fe[c0 + t], b = fn[c0 + t], c = force[c0 + t];
+            s_fe[t] = a;
+            s_fn[t] = b;
+            s_f[t] = c;
+            bad |= !(isfinite(a) && isfinite(b) && isfinite(c));
         }
-        __syncthreads();
+        poisoned |= __syncthreads_or(bad);
 #pragma unroll 2
         for (int j = lane; j < cn; j += 32) {
             const double fx = s_fe[j], fy = s_fn[j], fc = s_f[j];
@@ -116,6 +123,7 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
         double v = acc[p];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (MODE != 2 && (poisoned || !(isfinite(px[p]) && isfinite(py[p])))) v = __longlong_as_double(0x7ff8000000000000LL);
         if (lane == 0) s_out[warp * PTS + p] = v;
     }
     __syncthreads();
@@ -157,16 +165,22 @@ vb_predict2d_kernel(const double *__restrict__ east, const double *__restrict__ 
         ae[p] = 0.0;
         an[p] = 0.0;
     }
+    int poisoned = 0;
     for (int c0 = m0; c0 < m1; c0 += PRED2_CHUNK) {
         const int cn = min(PRED2_CHUNK, m1 - c0);
         __syncthreads();
+        int bad = 0;
         for (int t = threadIdx.x; t < cn; t += PRED_THREADS) {
-            s_fe[t] = fe[c0 + t];
-            s_fn[t] = fn[c0 + t];
-            s_f0[t] = force[c0 + t];            // east force j
-            s_f1[t] = force[m_total + c0 + t];  // north force j (verde/vector.py:456-457)
+            const double a = fe[c0 + t], b = fn[c0 + t];
+            const double c = force[c0 + t];            // east force j
+            const double d = force[m_total + c0 + t];  // north force j (verde/vector.py:456-457)
+            s_fe[t] = a;
+            s_fn[t] = b;
+            s_f0[t] = c;
+            s_f1[t] = d;
+            bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d));
         }
-        __syncthreads();
+        poisoned |= __syncthreads_or(bad);
         for (int j = lane; j < cn; j += 32) {
             const double fx = s_fe[j], fy = s_fn[j], f0 = s_f0[j], f1 = s_f1[j];
 #pragma unroll
@@ -188,6 +202,7 @@ vb_predict2d_kernel(const double *__restrict__ east, const double *__restrict__ 
             v += __shfl_xor_sync(0xffffffffu, v, off);
             w += __shfl_xor_sync(0xffffffffu, w, off);
         }
+        if (MODE != 2 && (poisoned || !(isfinite(px[p]) && isfinite(py[p])))) v = w = __longlong_as_double(0x7ff8000000000000LL);
         if (lane == 0) {
             s_out[warp * PTS + p] = v;
             s_out[PRED_WARPS * PTS + warp * PTS + p] = w;
@@ -296,7 +311,7 @@ cudaError_t vb_launch_predict(const double *e, const double *n, long long npts, 
     if (m == 0) return cudaMemsetAsync(out, 0, sizeof(double) * npts, stream);
     cudaError_t err = vb_init_tables();
     if (err != cudaSuccess) return err;
-    const int mode = exact ? 2 : (mindist != 0.0 ? 1 : 0);
+    const int mode = (exact || !(mindist >= 0.0)) ? 2 : (mindist != 0.0 ? 1 : 0);
     const int stride = (int)((m + nsplit - 1) / nsplit);
     dim3 grid((unsigned)((npts + (long long)PRED_WARPS * pts - 1) / ((long long)PRED_WARPS * pts)), nsplit);
     double *dst = nsplit > 1 ? scratch : out;
@@ -345,7 +360,7 @@ cudaError_t vb_launch_predict2d(const double *e, const double *n, long long npts
     }
     cudaError_t err = vb_init_tables();
     if (err != cudaSuccess) return err;
-    const int mode = exact ? 2 : (mindist != 0.0 ? 1 : 0);
+    const int mode = (exact || !(mindist >= 0.0)) ? 2 : (mindist != 0.0 ? 1 : 0);
     const int stride = (int)((m + nsplit - 1) / nsplit);
     if (pts > 4) pts = 4;  // two accumulators per point: keep register pressure bounded
     dim3 grid((unsigned)((npts + (long long)PRED_WARPS * pts - 1) / ((long long)PRED_WARPS * pts)), nsplit);
