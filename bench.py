@@ -210,13 +210,14 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world):
+def workload_config(world, n_rank=50_000, m=50_000, grid=2000):
+    base = "BASELINE configs[1]" if (n_rank, m, grid) == (50_000, 50_000, 2000) else "REDUCED-SIZE variant of configs[1]"
     return {
-        "workload": ("BASELINE configs[1]: Spline(damping=1e-6, mindist=1e-5), CheckerBoard scatter of 50k points, "
-                     "forces at data, grid 2000x2000" if world == 1 else
-                     "weak-scaled configs[1] (= configs[2] at N=8): {} data rows sharded over {} ranks, 50k forces, "
-                     "grid 2000x{} sharded".format(50_000 * world, world, 2000 * world)),
-        "n_data": 50_000 * world, "n_forces": 50_000, "grid_points": 2000 * 2000 * world,
+        "workload": ("{}: Spline(damping=1e-6, mindist=1e-5), CheckerBoard scatter of {} points, "
+                     "forces at data, grid {}x{}".format(base, n_rank, grid, grid) if world == 1 else
+                     "weak-scaled {} (= configs[2] at N=8 and full size): {} data rows sharded over {} ranks, {} forces, "
+                     "grid {}x{} sharded".format(base, n_rank * world, world, m, grid, grid * world)),
+        "n_data": n_rank * world, "n_forces": m, "grid_points": grid * grid * world,
         "damping": DAMPING, "mindist": MINDIST, "parallelism": "rows+grid sharded x{}".format(world),
         "l2": "inputs larger than L2 (10 GB Gram matrix streamed); no explicit flush",
     }
@@ -400,13 +401,13 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(world, n_rank, m, args.grid),
         "fit_s": fit_s, "predict_s": pred_s, "predict_gpts_per_s": (pb - pa) * world / pred_s * 1e-9,
         "predict_gpairs_per_s": n_pairs / pred_s * 1e-9,
         "fit_phases_ms": {k: phase["info"][k] for k in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms")},
         "fit_fp64_frac": algorithmic_fit_flops / fit_s * 1e-12 / peak if peak > 0 else None,
         "roofline": {
-            "kernel": "vb_gemm_tma_kernel (FP64 DMMA 128x128 tile kernel, TMA-bulk/mbarrier pipeline: Gram accumulation + Cholesky updates)",
+            "kernel": "vb_gemm_persistent_kernel (persistent FP64 DMMA 128x128 tile kernel, TMA-bulk/mbarrier pipeline: Gram accumulation + Cholesky updates)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak > 0 else None, "traffic": None,
             "peak_source": "FP64 DMMA.8x8x4 issue microbenchmark run in this process "

@@ -43,7 +43,7 @@ int fail(int code, const char *fmt, ...)
 // ---- options -------------------------------------------------------------------------
 struct Options {
     int predict_exact = 0;
-    int chol_panel_tiles = 4;
+    int chol_panel_tiles = 8;
     int gram_slab_chunks = 16;
 } g_opt;
 

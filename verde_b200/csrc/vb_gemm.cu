@@ -360,12 +360,120 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) vb_gemm_tma_kernel(const VbG
     }
 }
 
+// ===========================================================================
+// v3: persistent version of v2.  One CTA per SM loops over tiles (t = blockIdx.x,
+// += gridDim.x, so concurrently resident CTAs still work on neighbouring tiles).
+// The producer warp keeps streaming stages ACROSS tile boundaries, so the pipeline
+// never drains: no per-tile prologue bubble.  The epilogue cannot borrow the ring
+// (it is already filling with the next tile), so each consumer warp commits its
+// accumulators straight from registers with fire-and-forget RED.ADD.F64 (exactly
+// one add per element per launch -> still deterministic) and moves on.
+// ===========================================================================
+__global__ void __launch_bounds__(8 * 32 + 32, 1)
+vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
+{
+    constexpr int NCW = 8, MI = 8;
+    extern __shared__ __align__(128) double smem[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + V2_STAGES * V2_STAGE_DOUBLES);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int STEPS_PER_CHUNK = VB_TILE / V2_KC;
+    const int nsteps = p.nk * STEPS_PER_CHUNK;
+
+    if (tid == 0) {
+        for (int s = 0; s < V2_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[V2_STAGES + s]), NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    long long gstep = 0;  // ring position, continues across tiles
+    if (warp == NCW) {
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int bi, bj;
+            decode_tile(t, p.T, p.j_lo, p.j_hi, bi, bj);
+            const bool diag = (bi == bj) && (p.a_base == p.b_base);
+            const unsigned stage_bytes = (diag ? 1u : 2u) * V2_KC * VB_TILE * (unsigned)sizeof(double);
+            for (int step = 0; step < nsteps; ++step, ++gstep) {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[V2_STAGES + slot]), ph ^ 1u);
+                const unsigned full = smem_u32(&bars[slot]);
+                if (lane == 0) mbar_expect_tx(full, stage_bytes);
+                __syncwarp();
+                const int kk = step / STEPS_PER_CHUNK;
+                const int krow0 = (step % STEPS_PER_CHUNK) * V2_KC;
+                double *sA = smem + slot * V2_STAGE_DOUBLES;
+                double *sB = sA + V2_KC * LDS_STRIDE;
+                const double *gA = p.a_base + p.a_chunk_off[kk] + (long long)bj * VB_TILE_ELEMS + krow0 * VB_TILE;
+                const double *gB = p.b_base + p.b_chunk_off[kk] + (long long)bi * VB_TILE_ELEMS + krow0 * VB_TILE;
+                bulk_load(smem_u32(sA + lane * LDS_STRIDE), gA + lane * VB_TILE, VB_TILE * sizeof(double), full);
+                if (!diag)
+                    bulk_load(smem_u32(sB + lane * LDS_STRIDE), gB + lane * VB_TILE, VB_TILE * sizeof(double), full);
+            }
+        }
+    } else {
+        const int p0 = (warp >> 2) * (MI * 8);
+        const int q0 = (warp & 3) * 32;
+        const int lk = lane & 3, lr = lane >> 2;
+        const double alpha = p.alpha;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int bi, bj;
+            decode_tile(t, p.T, p.j_lo, p.j_hi, bi, bj);
+            const bool diag = (bi == bj) && (p.a_base == p.b_base);
+            double acc[MI][4][2];
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int step = 0; step < nsteps; ++step, ++gstep) {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[slot]), ph);
+                const double *sA = smem + slot * V2_STAGE_DOUBLES;
+                const double *sB = diag ? sA : sA + V2_KC * LDS_STRIDE;
+#pragma unroll
+                for (int k4 = 0; k4 < V2_KC / 4; ++k4) {
+                    const double *ra = sA + (k4 * 4 + lk) * LDS_STRIDE + p0 + lr;
+                    const double *rb = sB + (k4 * 4 + lk) * LDS_STRIDE + q0 + lr;
+                    double fa[MI], fb[4];
+#pragma unroll
+                    for (int a = 0; a < MI; ++a) fa[a] = ra[a * 8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) fb[b] = rb[b * 8];
+#pragma unroll
+                    for (int a = 0; a < MI; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[V2_STAGES + slot]));
+            }
+            double *ctile = p.c_base + vb_tile_index(bi, bj, p.T) * VB_TILE_ELEMS;
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double *dst = ctile + (p0 + 8 * a + lr) * VB_TILE + q0 + 8 * b + 2 * lk;
+                    if (p.accumulate) {
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(alpha * acc[a][b][0]) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 1), "d"(alpha * acc[a][b][1]) : "memory");
+                    } else {
+                        *reinterpret_cast<double2 *>(dst) = make_double2(alpha * acc[a][b][0], alpha * acc[a][b][1]);
+                    }
+                }
+        }
+    }
+}
+
 }  // namespace
 
 long long vb_launch_counter = 0;
 // 0: v1 (cp.async + __syncthreads); 1: v2 (TMA bulk + mbarrier + bulk reduce), 8 consumer warps;
-// 2: v2 with 16 consumer warps (32x32 warp tiles)
-int vb_gemm_variant = 1;
+// 2: v2 with 16 consumer warps (32x32 warp tiles); 3: v3 persistent (producer run-ahead, RED epilogue)
+int vb_gemm_variant = 3;
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi)
 {
@@ -387,6 +495,17 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream)
         e = cudaFuncSetAttribute(vb_gemm_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         vb_gemm_tma_kernel<8><<<(unsigned)tiles, 8 * 32 + 32, V2_SMEM_BYTES, stream>>>(p);
+    } else if (vb_gemm_variant == 3) {
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        }
+        e = cudaFuncSetAttribute(vb_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+        vb_gemm_persistent_kernel<<<grid, 8 * 32 + 32, V2_SMEM_BYTES, stream>>>(p, tiles);
     } else if (vb_gemm_variant == 2) {
         e = cudaFuncSetAttribute(vb_gemm_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
         if (e != cudaSuccess) return e;
