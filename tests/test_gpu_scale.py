@@ -62,7 +62,7 @@ def test_row_sharded_accumulation_equals_single_pass(env):
     p0, p1 = np.empty(500), np.empty(500)
     kernels.predict_b200(e[:500], nn[:500], fe, fn, 1e-5, f0, p0)
     kernels.predict_b200(e[:500], nn[:500], fe, fn, 1e-5, f1, p1)
-    assert np.max(np.abs(p1 - p0)) < 1e-8 * np.ptp(d)
+    assert np.max(np.abs(p1 - p0)) < 1e-6 * np.ptp(d)
 
 
 def test_backward_error_of_the_solve_at_20k(env):

@@ -10,6 +10,7 @@ from . import dist  # noqa: F401
 from ._cabi import EngineError  # noqa: F401
 from .base import BaseGridder, GridResult, check_fit_input, n_1d_arrays, score_estimator  # noqa: F401
 from .checkerboard import CheckerBoard  # noqa: F401
+from .compose import Chain, Vector  # noqa: F401
 from .coords import (  # noqa: F401
     get_region,
     grid_coordinates,

@@ -298,6 +298,9 @@ int vb200_set_option(const char *key, double value)
     else if (k == "chol_panel_tiles") g_opt.chol_panel_tiles = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "gram_slab_chunks") g_opt.gram_slab_chunks = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
+    else if (k == "gemm_strip") vb_gemm_strip = (int)value;
+    else if (k == "predict_minb") vb_predict_minb = (int)value;
+    else if (k == "predict_pts") vb_predict_pts = (int)value;
     else return fail(VB200_E_BADARG, "unknown option '%s'", key);
     return 0;
 }

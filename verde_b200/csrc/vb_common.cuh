@@ -68,47 +68,43 @@ __device__ __forceinline__ void vb_greens2d_exact(double dx, double dy, double m
 // ---------------------------------------------------------------------------
 // Green's functions, "fast" flavour for the O(N*M) matrix-free predict, where
 // the FP64 pipe is the roofline (36.8 TFLOP/s DFMA measured; libdevice log costs
-// ~50 FP64 issue slots, sqrt ~16).  Table-driven log (no division) + Goldschmidt
-// sqrt seeded by MUFU.RSQ64H: ~11 + ~7 FP64 slots.  Accuracy: |log error| <=
+// ~50 FP64 issue slots, sqrt ~16).  Table-driven log (no division, 8 slots) + a
+// third-order sqrt correction of the MUFU.RSQ64H seed (5 slots).  Accuracy: |log error| <=
 // ~2e-16 * max(1, |log d|) absolute, which bounds the Green's value error by a
 // few eps * d^2 * max(1, |log d|)  (tests/test_gpu_greens.py pins this against
 // the exact flavour and the oracle).
 // ---------------------------------------------------------------------------
-#define VB_LOGTAB_ENTRIES 128
-// smem layout: entry idx is replicated 8x at byte offset idx*128 + (lane%8)*16
-// so that the 8 lanes of a quarter-warp always hit 8 different 16-byte slots:
-// one LDS.128 per evaluation, never a bank conflict.
-#define VB_LOGTAB_SMEM_DOUBLES (VB_LOGTAB_ENTRIES * 16)
+#define VB_LOGTAB_ENTRIES 1024
+// smem layout: the plain table, 16 bytes per entry {1/c_k, log c_k}, c_k = 1 + (k + 0.5)/1024.
+// One LDS.128 per evaluation at a data-dependent index: ~2.5-way bank conflicts on average,
+// which the (otherwise idle) LSU pipe absorbs; in exchange |r| <= 2^-11 and log1p needs only
+// a degree-4 polynomial (truncation r^5/5 <= 2^-57 absolute).
+#define VB_LOGTAB_SMEM_DOUBLES (VB_LOGTAB_ENTRIES * 2)
 
-// gtab: global copy of the base table {rcp_c, log_c} (filled by vb_init_tables()).
+// gtab: global copy of the table (filled by vb_init_tables()).
 __device__ __forceinline__ void vb_logtab_stage(double *smem_tab, const double2 *gtab)
 {
     // called by all threads of a CTA; caller syncs afterwards
-    for (int t = threadIdx.x; t < VB_LOGTAB_ENTRIES * 8; t += blockDim.x) {
-        const double2 v = gtab[t >> 3];
-        reinterpret_cast<double2 *>(smem_tab)[t] = v;
-    }
+    for (int t = threadIdx.x; t < VB_LOGTAB_ENTRIES; t += blockDim.x)
+        reinterpret_cast<double2 *>(smem_tab)[t] = gtab[t];
 }
 
-// log(d) for normal positive d.  `tab` points at this lane's replica column:
-// reinterpret_cast<const double2*>(smem_tab) + (lane & 7).  Never produces inf/NaN:
+// log(d) for normal positive d; `tab` is the shared-memory table.  Never produces inf/NaN:
 // d = 0 reads as 2^-1023 (finite log), so r2 * log(r2) is an exact 0 at r2 = 0.
+// 8 FP64 issue slots: 1 (exponent) + 1 (r) + 2 (Horner) + 1 (r^2) + 1 + 2 (assembly).
 __device__ __forceinline__ double vb_log_fast(double d, const double2 *tab)
 {
     const int hi = __double2hiint(d);
     const int lo = __double2loint(d);
-    // byte offset of table entry idx = mantissa bits 19..13: idx * 128
-    const int off = (hi >> 6) & 0x3F80;
+    // byte offset of table entry idx = mantissa bits 19..10: idx * 16
+    const int off = (hi >> 6) & 0x3FF0;
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // double(biased exponent - 1023) without an I2F: 2^52 + biased as a bit pattern
     const double ed = __hiloint2double(0x43300000, (unsigned)hi >> 20) - 4503599627371519.0;
     const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(tab) + off);
     const double r = fma(m, t.x, -1.0);
-    // log1p(r), |r| <= 2^-8: r - r^2/2 + ... + r^7/7
-    double q = fma(r, 1.0 / 7.0, -1.0 / 6.0);
-    q = fma(r, q, 1.0 / 5.0);
-    q = fma(r, q, -1.0 / 4.0);
-    q = fma(r, q, 1.0 / 3.0);
+    // log1p(r), |r| <= 2^-11: r - r^2/2 + r^3/3 - r^4/4
+    double q = fma(r, -0.25, 1.0 / 3.0);
     q = fma(r, q, -0.5);
     const double r2 = r * r;
     const double l1p = fma(r2, q, r);
@@ -143,8 +139,8 @@ __device__ __forceinline__ double vb_rcp_fast(double x)
 // d^2 (log d - 1) with d = sqrt(dx^2+dy^2) + mindist, for FINITE inputs (the predict
 // kernels screen non-finite coordinates / forces outside their inner loop).
 //   HAS_MINDIST = false folds the sqrt away: r2 * (0.5*log(r2) - 1), exactly 0 at r2 = 0
-//   (18 FP64 slots per pair); HAS_MINDIST = true adds 1e-300 to r2 inside the FMA chain so the
-//   rsqrt seed never sees 0 (sqrt -> 1e-150, absorbed by any mindist > 1e-134): 25 slots.
+//   (15 FP64 slots per pair); HAS_MINDIST = true adds 1e-300 to r2 inside the FMA chain so the
+//   rsqrt seed never sees 0 (sqrt -> 1e-150, absorbed by any mindist > 1e-134): 22 slots.
 #define VB_R2_FLOOR 1e-300
 template <bool HAS_MINDIST>
 __device__ __forceinline__ double vb_greens_fast(double dx, double dy, double mindist,

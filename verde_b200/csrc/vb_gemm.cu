@@ -27,7 +27,6 @@ constexpr int KC = 16;                 // k rows per pipeline stage
 constexpr int LDS_STRIDE = VB_TILE + 4;  // doubles per padded smem row
 constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 256;
-constexpr int STRIP = 8;  // block columns per rasterisation strip
 constexpr int STAGE_DOUBLES = 2 * KC * LDS_STRIDE;
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
 
@@ -54,7 +53,7 @@ __host__ __device__ __forceinline__ long long strip_tiles(int T, int c0, int w)
 }
 
 // linear tile id -> (bi, bj)
-__device__ __forceinline__ void decode_tile(long long t, int T, int j_lo, int j_hi, int &bi, int &bj)
+__device__ __forceinline__ void decode_tile(long long t, int T, int j_lo, int j_hi, int STRIP, int &bi, int &bj)
 {
     int c0 = j_lo;
     int w = min(STRIP, j_hi - c0);
@@ -87,7 +86,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) vb_gemm_kernel(const VbGemmPa
     extern __shared__ __align__(16) double smem[];
 
     int bi, bj;
-    decode_tile(blockIdx.x, p.T, p.j_lo, p.j_hi, bi, bj);
+    decode_tile(blockIdx.x, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
     const bool diag = (bi == bj) && (p.a_base == p.b_base);
 
     const int tid = threadIdx.x;
@@ -260,7 +259,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) vb_gemm_tma_kernel(const VbG
     // bars[0..S) = full, bars[S..2S) = empty
 
     int bi, bj;
-    decode_tile(blockIdx.x, p.T, p.j_lo, p.j_hi, bi, bj);
+    decode_tile(blockIdx.x, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
     const bool diag = (bi == bj) && (p.a_base == p.b_base);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -393,7 +392,7 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
     if (warp == NCW) {
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
             int bi, bj;
-            decode_tile(t, p.T, p.j_lo, p.j_hi, bi, bj);
+            decode_tile(t, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
             const bool diag = (bi == bj) && (p.a_base == p.b_base);
             const unsigned stage_bytes = (diag ? 1u : 2u) * V2_KC * VB_TILE * (unsigned)sizeof(double);
             for (int step = 0; step < nsteps; ++step, ++gstep) {
@@ -421,7 +420,7 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
         const double alpha = p.alpha;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
             int bi, bj;
-            decode_tile(t, p.T, p.j_lo, p.j_hi, bi, bj);
+            decode_tile(t, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
             const bool diag = (bi == bj) && (p.a_base == p.b_base);
             double acc[MI][4][2];
 #pragma unroll
@@ -474,19 +473,20 @@ long long vb_launch_counter = 0;
 // 0: v1 (cp.async + __syncthreads); 1: v2 (TMA bulk + mbarrier + bulk reduce), 8 consumer warps;
 // 2: v2 with 16 consumer warps (32x32 warp tiles); 3: v3 persistent (producer run-ahead, RED epilogue)
 int vb_gemm_variant = 3;
+int vb_gemm_strip = 16;  // block columns per rasterisation strip (L2 reuse of the column panels)
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi)
 {
+    // sum over block columns j_lo..j_hi-1 of the column heights (T - c): independent of the strip width
     long long total = 0;
-    for (int c0 = j_lo; c0 < j_hi; c0 += STRIP) {
-        const int w = (j_hi - c0 < STRIP) ? (j_hi - c0) : STRIP;
-        total += strip_tiles(T, c0, w);
-    }
+    for (int c = j_lo; c < j_hi; ++c) total += T - c;
     return total;
 }
 
-cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream)
+cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
 {
+    VbGemmParams p = p_in;
+    p.strip = vb_gemm_strip < 1 ? 1 : vb_gemm_strip;
     if (p.nk <= 0 || p.nk > VB_MAX_KCHUNKS) return cudaErrorInvalidValue;
     const long long tiles = vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
     if (tiles <= 0) return cudaSuccess;

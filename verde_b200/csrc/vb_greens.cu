@@ -60,8 +60,8 @@ constexpr int PRED_CHUNK = 1024;  // forces staged per pass: 3 * 8 KB
 constexpr int PRED2_CHUNK = 512;  // 2-D kernel stages 4 arrays; static smem limit is 48 KB
 
 // MODE 0: fast Green's, mindist == 0; MODE 1: fast, mindist != 0; MODE 2: exact.
-template <int PTS, int MODE>
-__global__ void __launch_bounds__(PRED_THREADS)
+template <int PTS, int MODE, int MINB>
+__global__ void __launch_bounds__(PRED_THREADS, MINB)
 vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ north, long long npts,
                   const double *__restrict__ fe, const double *__restrict__ fn,
                   const double *__restrict__ force, int m_begin_stride, int m_total,
@@ -73,7 +73,7 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (MODE != 2) vb_logtab_stage(s_tab, vb_logtab_global);
-    const double2 *tab = reinterpret_cast<const double2 *>(s_tab) + (lane & 7);
+    const double2 *tab = reinterpret_cast<const double2 *>(s_tab);
 
     // force range of this split (blockIdx.y): [m0, m1)
     const int m0 = min(m_total, (int)blockIdx.y * m_begin_stride);
@@ -149,7 +149,7 @@ vb_predict2d_kernel(const double *__restrict__ east, const double *__restrict__ 
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (MODE != 2) vb_logtab_stage(s_tab, vb_logtab_global);
-    const double2 *tab = reinterpret_cast<const double2 *>(s_tab) + (lane & 7);
+    const double2 *tab = reinterpret_cast<const double2 *>(s_tab);
     const double c3 = 3.0 - poisson, c1 = 1.0 + poisson;
 
     const int m0 = min(m_total, (int)blockIdx.y * m_begin_stride);
@@ -282,8 +282,32 @@ void vb_predict_plan(long long npts, long long m, int *pts, int *nsplit)
     long long blocks = (npts + (long long)PRED_WARPS * p - 1) / ((long long)PRED_WARPS * p);
     int s = 1;
     while (blocks * s < 2 * 148 && m / (s * 2) >= 2 * PRED_CHUNK && s < 64) s *= 2;
+    if (vb_predict_pts == 1 || vb_predict_pts == 2 || vb_predict_pts == 4 || vb_predict_pts == 8) {
+        p = vb_predict_pts;
+        blocks = (npts + (long long)PRED_WARPS * p - 1) / ((long long)PRED_WARPS * p);
+        s = 1;
+        while (blocks * s < 2 * 148 && m / (s * 2) >= 2 * PRED_CHUNK && s < 64) s *= 2;
+    }
     *pts = p;
     *nsplit = s;
+}
+
+int vb_predict_minb = 2;  // resident CTAs per SM the scalar predict kernel is compiled for (2..4)
+int vb_predict_pts = 0;   // 0 = choose from the problem size
+
+template <int PTS, int MINB>
+static cudaError_t launch_predict_pts_minb(int mode, dim3 grid, const double *e, const double *n,
+                                           long long npts, const double *fe, const double *fn,
+                                           const double *f, int stride, int m, double mindist,
+                                           double *out, cudaStream_t stream)
+{
+    if (mode == 0)
+        vb_predict_kernel<PTS, 0, MINB><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    else if (mode == 1)
+        vb_predict_kernel<PTS, 1, MINB><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    else
+        vb_predict_kernel<PTS, 2, 2><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    return cudaGetLastError();
 }
 
 template <int PTS>
@@ -292,13 +316,11 @@ static cudaError_t launch_predict_pts(int mode, dim3 grid, const double *e, cons
                                       const double *f, int stride, int m, double mindist,
                                       double *out, cudaStream_t stream)
 {
-    if (mode == 0)
-        vb_predict_kernel<PTS, 0><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
-    else if (mode == 1)
-        vb_predict_kernel<PTS, 1><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
-    else
-        vb_predict_kernel<PTS, 2><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
-    return cudaGetLastError();
+    if (vb_predict_minb >= 4)
+        return launch_predict_pts_minb<PTS, 4>(mode, grid, e, n, npts, fe, fn, f, stride, m, mindist, out, stream);
+    if (vb_predict_minb == 3)
+        return launch_predict_pts_minb<PTS, 3>(mode, grid, e, n, npts, fe, fn, f, stride, m, mindist, out, stream);
+    return launch_predict_pts_minb<PTS, 2>(mode, grid, e, n, npts, fe, fn, f, stride, m, mindist, out, stream);
 }
 
 // scratch: nsplit*npts doubles when nsplit > 1 (may be null otherwise)

@@ -22,6 +22,7 @@ struct VbGemmParams {
     int j_lo, j_hi;
     double alpha;
     int accumulate;  // 0: C = alpha*acc, 1: C += alpha*acc
+    int strip;       // rasterisation strip width in block columns (filled by vb_launch_gemm)
 };
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
@@ -31,7 +32,9 @@ cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t stream);
 // every kernel launch of the library bumps this (the bench's gpu_launches claim)
 extern long long vb_launch_counter;
 // DMMA tile kernel flavour (see vb_gemm.cu)
-extern int vb_gemm_variant;
+extern int vb_gemm_variant, vb_gemm_strip;
+// predict kernel tuning knobs (vb_greens.cu)
+extern int vb_predict_minb, vb_predict_pts;
 
 cudaError_t vb_init_tables();
 cudaError_t vb_launch_jacobian(const double *e, const double *n, long long npts, const double *fe,
