@@ -257,6 +257,9 @@ def main():
     lib.vb200_set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints "NCCL version ..." on STDOUT at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n_rank, m = args.size, args.size if world == 1 else min(50_000, args.size)
