@@ -246,6 +246,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # Libraries (NCCL's "NCCL version ..." banner) write to STDOUT; the contract is ONE JSON line there.
+    # Park the real stdout and point fd 1 at stderr until the line is ready.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as td
 
@@ -431,7 +437,8 @@ def main():
                        "n*m, n*m^2, m^3/3, N*M scaling").format(args.cpu_sample, cpu["sample_seconds"]),
             "fit_s_extrapolated": cpu["fit_s_extrapolated"], "predict_gpairs_per_s": cpu["predict_gpairs_per_s"],
         }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         td.destroy_process_group()
 
