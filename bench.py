@@ -234,7 +234,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=50_000, help="data points per rank (default: the BASELINE 50k)")
     ap.add_argument("--grid", type=int, default=2000, help="grid is GRID x GRID per rank")
-    ap.add_argument("--cpu-sample", type=int, default=8000, help="n=m of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=14000, help="n=m of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
