@@ -1,0 +1,78 @@
+"""
+Keeps the selectable kernel flavours honest: every DMMA tile-kernel generation (v1 cp.async,
+v2 TMA/mbarrier, v2 with 16 consumer warps, v3 persistent) must produce the same normal matrix and
+forces, and the fused in-shared-memory Gram variant must reproduce the staged Gram matrix to the
+accuracy of the fast Green's function.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import verde_b200 as vb
+    from verde_b200 import _cabi, kernels
+
+    return vb, kernels, _cabi.require_device()
+
+
+def sample(n, seed=0):
+    rng = np.random.RandomState(seed)
+    e, nn = rng.uniform(0, 5000, n), rng.uniform(-5000, 0, n)
+    return e, nn, 1000.0 * np.sin(e / 400.0) * np.cos(nn / 400.0)
+
+
+def test_gemm_generations_agree(env):
+    vb, kernels, lib = env
+    e, nn, d = sample(1100)
+    w = np.random.RandomState(1).uniform(0.5, 2, e.size)
+    results = {}
+    try:
+        for variant in (3, 0, 1, 2):
+            assert lib.vb200_set_option(b"gemm_variant", float(variant)) == 0
+            system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, w, e, nn, 1e-5)
+            gram = system.gram.cpu().numpy()
+            results[variant] = (gram, system.solve(e.size, 1e-3))
+    finally:
+        lib.vb200_set_option(b"gemm_variant", 3.0)
+    g_ref, f_ref = results[3]
+    for variant in (0, 1, 2):
+        gram, force = results[variant]
+        np.testing.assert_allclose(gram, g_ref, rtol=1e-13, atol=1e-13 * np.abs(g_ref).max())
+        assert np.max(np.abs(force - f_ref)) <= 1e-9 * np.max(np.abs(f_ref)), variant
+
+
+@pytest.mark.parametrize("mindist,weighted", [(0.0, False), (1e-5, True)])
+def test_fused_in_smem_gram_matches_staged(env, mindist, weighted):
+    vb, kernels, lib = env
+    e, nn, d = sample(900, seed=3)
+    fe, fn, _ = sample(300, seed=4)
+    w = np.random.RandomState(2).uniform(0.5, 2, e.size) if weighted else None
+    staged = kernels.GramSystem(fe.size).accumulate(0, e, nn, d, w, fe, fn, mindist)
+    try:
+        assert lib.vb200_set_option(b"gram_fused", 1.0) == 0
+        fused = kernels.GramSystem(fe.size).accumulate(0, e, nn, d, w, fe, fn, mindist)
+    finally:
+        lib.vb200_set_option(b"gram_fused", 0.0)
+    g0, g1 = staged.gram.cpu().numpy(), fused.gram.cpu().numpy()
+    # tile-packed lower triangle; compare on the scale of the diagonal (entries span many decades)
+    assert np.max(np.abs(g1 - g0)) <= 1e-12 * np.abs(g0).max()
+    np.testing.assert_array_equal(staged.stats.cpu().numpy(), fused.stats.cpu().numpy())
+    f0, f1 = staged.solve(e.size, 1e-2), fused.solve(e.size, 1e-2)
+    assert np.max(np.abs(f1 - f0)) <= 1e-6 * np.max(np.abs(f0))
+
+
+def test_chol_panel_width_does_not_change_the_solution(env):
+    vb, kernels, lib = env
+    e, nn, d = sample(1500, seed=5)
+    forces = []
+    try:
+        for width in (1, 3, 8):
+            assert lib.vb200_set_option(b"chol_panel_tiles", float(width)) == 0
+            forces.append(kernels.fit_spline(e, nn, d, None, e, nn, 0.0, 1e-2))
+    finally:
+        lib.vb200_set_option(b"chol_panel_tiles", 8.0)
+    for f in forces[1:]:
+        assert np.max(np.abs(f - forces[0])) <= 1e-8 * np.max(np.abs(forces[0]))

@@ -45,6 +45,7 @@ struct Options {
     int predict_exact = 0;
     int chol_panel_tiles = 8;
     int gram_slab_chunks = 16;
+    int gram_fused = 0;
 } g_opt;
 
 // ---- cached workspace (grow-only, per process; one process per GPU) --------------------
@@ -297,6 +298,7 @@ int vb200_set_option(const char *key, double value)
     if (k == "predict_exact") g_opt.predict_exact = value != 0.0;
     else if (k == "chol_panel_tiles") g_opt.chol_panel_tiles = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "gram_slab_chunks") g_opt.gram_slab_chunks = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
+    else if (k == "gram_fused") g_opt.gram_fused = value != 0.0;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
     else if (k == "predict_minb") vb_predict_minb = (int)value;
@@ -505,11 +507,44 @@ static int gram_accumulate_impl(int kind, const double *jac, const double *east,
     if (chunks == 0 && !accumulate)
         CU(cudaMemsetAsync(gram_dev, 0, sizeof(double) * vb200_gram_doubles(cols), st));
     const int slab = g_opt.gram_slab_chunks;
+    const bool fused = g_opt.gram_fused && kind == 0 && chunks > 0;
     double *panel = nullptr;
-    if (chunks > 0)
+    if (chunks > 0 && !fused)
         CU(ws_get("panel", sizeof(double) * (size_t)(chunks < slab ? chunks : slab) * T * VB_TILE_ELEMS, (void **)&panel));
     const long long launches0 = vb_launch_counter;
-    for (long long c0 = 0; c0 < chunks; c0 += slab) {
+    if (fused) {
+        // measured alternative: statistics in a generation-only pass, then ONE
+        // persistent kernel that generates Jacobian rows in shared memory and feeds the DMMA tiles
+        for (long long c0 = 0; c0 < chunks; c0 += slab) {
+            const int nch = (int)((chunks - c0 < slab) ? (chunks - c0) : slab);
+            CU(vb_launch_gram_panel(pb, c0 * VB_TILE, nch, T, nullptr, stats_dev, st));
+        }
+        VbFusedGramParams f = {};
+        f.east = pb.east;
+        f.north = pb.north;
+        f.n = pb.n;
+        f.fe = pb.fe;
+        f.fn = pb.fn;
+        f.m = pb.m;
+        f.mindist = pb.mindist;
+        f.c_base = gram_dev;
+        f.T = T;
+        f.accumulate = accumulate ? 1 : 0;
+        if (pb.weights) {
+            double *sw;
+            CU(ws_get("sqrt_w", sizeof(double) * rows, (void **)&sw));
+            CU(vb_launch_sqrt(pb.weights, rows, sw, st));
+            f.sqrt_w = sw;
+        }
+        Span sp;
+        CU(span_begin(&sp, st));
+        CU(vb_launch_fused_gram(f, st));
+        CU(cudaEventRecord(sp.b, st));
+        g_prof.gemm.push_back(sp);
+        g_prof.gemm_flops += 2.0 * VB_TILE * VB_TILE * (double)rows * (double)vb_gemm_num_tiles(T, 0, T);
+        g_prof.launches += 1;
+    }
+    for (long long c0 = 0; c0 < chunks && !fused; c0 += slab) {
         const int nch = (int)((chunks - c0 < slab) ? (chunks - c0) : slab);
         CU(vb_launch_gram_panel(pb, c0 * VB_TILE, nch, T, panel, stats_dev, st));
         VbGemmParams g = {};

@@ -467,6 +467,131 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
     }
 }
 
+// ===========================================================================
+// Fused in-shared-memory Gram (the literal north_star form): no Jacobian panel
+// anywhere in HBM.  Same persistent consumer pipeline as v3, but the stages are
+// PRODUCED by four generator warps that evaluate the Green's function
+// (fast flavour: 21 FP64 slots per entry) straight into the padded operand
+// rows; full[] barriers count generator-thread arrivals instead of TMA bytes.
+// Kept as a measured alternative: DMMA and DFMA share one pipe on sm_100a, so
+// regenerating 2*128 entries per 128x128 MACs per data row costs >= 33% extra
+// FP64 issue on top of the matrix product.
+// ===========================================================================
+constexpr int FG_GEN_WARPS = 4;
+constexpr int FG_THREADS = 8 * 32 + FG_GEN_WARPS * 32;
+constexpr int FG_SMEM_BYTES = V2_RING_BYTES + VB_LOGTAB_SMEM_DOUBLES * (int)sizeof(double) + 64;
+
+template <bool HAS_MINDIST>
+__global__ void __launch_bounds__(FG_THREADS, 1)
+vb_fused_gram_kernel(const VbFusedGramParams p, long long ntiles, const double2 *__restrict__ gtab)
+{
+    constexpr int NCW = 8, MI = 8;
+    extern __shared__ __align__(128) double smem[];
+    double *s_tab = smem + V2_STAGES * V2_STAGE_DOUBLES;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_tab + VB_LOGTAB_SMEM_DOUBLES);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nsteps = (int)((p.n + V2_KC - 1) / V2_KC);
+
+    vb_logtab_stage(s_tab, gtab);
+    if (tid == 0) {
+        for (int s = 0; s < V2_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), FG_GEN_WARPS * 32);  // every generator thread arrives
+            mbar_init(smem_u32(&bars[V2_STAGES + s]), NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    long long gstep = 0;
+    if (warp >= NCW) {
+        // ---------------- generator warps: thread g owns column g of both operand blocks ----------------
+        const int g = tid - NCW * 32;
+        const double2 *tab = reinterpret_cast<const double2 *>(s_tab);
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int bi, bj;
+            decode_tile(t, p.T, 0, p.T, p.strip, bi, bj);
+            const bool diag = bi == bj;
+            const long long ca = (long long)bj * VB_TILE + g, cb = (long long)bi * VB_TILE + g;
+            const bool va = ca < p.m, vb = cb < p.m;
+            const double fxa = va ? p.fe[ca] : 0.0, fya = va ? p.fn[ca] : 0.0;
+            const double fxb = vb ? p.fe[cb] : 0.0, fyb = vb ? p.fn[cb] : 0.0;
+            for (int step = 0; step < nsteps; ++step, ++gstep) {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[V2_STAGES + slot]), ph ^ 1u);
+                double *sA = smem + slot * V2_STAGE_DOUBLES;
+                double *sB = sA + V2_KC * LDS_STRIDE;
+                const long long r0 = (long long)step * V2_KC;
+#pragma unroll 4
+                for (int k = 0; k < V2_KC; ++k) {
+                    const long long row = r0 + k;
+                    const bool vr = row < p.n;
+                    const double ex = vr ? p.east[row] : 0.0, ny = vr ? p.north[row] : 0.0;
+                    const double sw = vr ? (p.sqrt_w ? p.sqrt_w[row] : 1.0) : 0.0;
+                    double ga = vb_greens_fast<HAS_MINDIST>(ex - fxa, ny - fya, p.mindist, tab) * sw;
+                    sA[k * LDS_STRIDE + g] = va ? ga : 0.0;
+                    if (!diag) {
+                        double gb = vb_greens_fast<HAS_MINDIST>(ex - fxb, ny - fyb, p.mindist, tab) * sw;
+                        sB[k * LDS_STRIDE + g] = vb ? gb : 0.0;
+                    }
+                }
+                mbar_arrive(smem_u32(&bars[slot]));
+            }
+        }
+    } else {
+        const int p0 = (warp >> 2) * (MI * 8);
+        const int q0 = (warp & 3) * 32;
+        const int lk = lane & 3, lr = lane >> 2;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int bi, bj;
+            decode_tile(t, p.T, 0, p.T, p.strip, bi, bj);
+            const bool diag = bi == bj;
+            double acc[MI][4][2];
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int step = 0; step < nsteps; ++step, ++gstep) {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[slot]), ph);
+                const double *sA = smem + slot * V2_STAGE_DOUBLES;
+                const double *sB = diag ? sA : sA + V2_KC * LDS_STRIDE;
+#pragma unroll
+                for (int k4 = 0; k4 < V2_KC / 4; ++k4) {
+                    const double *ra = sA + (k4 * 4 + lk) * LDS_STRIDE + p0 + lr;
+                    const double *rb = sB + (k4 * 4 + lk) * LDS_STRIDE + q0 + lr;
+                    double fa[MI], fb[4];
+#pragma unroll
+                    for (int a = 0; a < MI; ++a) fa[a] = ra[a * 8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) fb[b] = rb[b * 8];
+#pragma unroll
+                    for (int a = 0; a < MI; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[V2_STAGES + slot]));
+            }
+            double *ctile = p.c_base + vb_tile_index(bi, bj, p.T) * VB_TILE_ELEMS;
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double *dst = ctile + (p0 + 8 * a + lr) * VB_TILE + q0 + 8 * b + 2 * lk;
+                    if (p.accumulate) {
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(acc[a][b][0]) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 1), "d"(acc[a][b][1]) : "memory");
+                    } else {
+                        *reinterpret_cast<double2 *>(dst) = make_double2(acc[a][b][0], acc[a][b][1]);
+                    }
+                }
+        }
+    }
+}
+
 }  // namespace
 
 long long vb_launch_counter = 0;
@@ -514,6 +639,35 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
         e = cudaFuncSetAttribute(vb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         vb_gemm_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    }
+    ++vb_launch_counter;
+    return cudaGetLastError();
+}
+
+// defined in vb_greens.cu: device address of the log table used by the fast Green's function
+const double2 *vb_logtab_device_ptr();
+
+cudaError_t vb_launch_fused_gram(const VbFusedGramParams &p_in, cudaStream_t stream)
+{
+    VbFusedGramParams p = p_in;
+    p.strip = vb_gemm_strip < 1 ? 1 : vb_gemm_strip;
+    cudaError_t e = vb_init_tables();
+    if (e != cudaSuccess) return e;
+    const long long tiles = vb_gemm_num_tiles(p.T, 0, p.T);
+    if (tiles <= 0 || p.n <= 0) return cudaSuccess;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    const double2 *gtab = vb_logtab_device_ptr();
+    if (p.mindist != 0.0) {
+        e = cudaFuncSetAttribute(vb_fused_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FG_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        vb_fused_gram_kernel<true><<<grid, FG_THREADS, FG_SMEM_BYTES, stream>>>(p, tiles, gtab);
+    } else {
+        e = cudaFuncSetAttribute(vb_fused_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FG_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        vb_fused_gram_kernel<false><<<grid, FG_THREADS, FG_SMEM_BYTES, stream>>>(p, tiles, gtab);
     }
     ++vb_launch_counter;
     return cudaGetLastError();

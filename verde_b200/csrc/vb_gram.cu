@@ -70,7 +70,7 @@ vb_gram_panel_kernel(const VbGramProblem pb, long long row0, int nchunk, int T, 
                 sb = fma(w * j, pb.data[r], sb);
                 v = pb.weights ? sqrt(w) * j : j;
             }
-            dst[k * VB_TILE + i] = v;
+            if (panel) dst[k * VB_TILE + i] = v;  // panel == nullptr: statistics-only pass (fused Gram variant)
         }
     }
     s_red[0][threadIdx.x] = sb;
@@ -141,6 +141,20 @@ cudaError_t vb_launch_gram_panel(const VbGramProblem &prob, long long row0, int 
 {
     vb_gram_panel_kernel<<<T, GEN_THREADS, 0, stream>>>(prob, row0, nchunk, T, (long long)T * VB_TILE,
                                                         panel, stats);
+    ++vb_launch_counter;
+    return cudaGetLastError();
+}
+
+__global__ void vb_sqrt_kernel(const double *__restrict__ w, long long n, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrt(w[i]);
+}
+
+cudaError_t vb_launch_sqrt(const double *w, long long n, double *out, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    vb_sqrt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, n, out);
     ++vb_launch_counter;
     return cudaGetLastError();
 }

@@ -236,6 +236,13 @@ __global__ void vb_reduce_splits_kernel(const double *__restrict__ part, long lo
 // ---------------------------------------------------------------------------
 static int g_tables_ready = 0;
 
+const double2 *vb_logtab_device_ptr()
+{
+    void *ptr = nullptr;
+    cudaGetSymbolAddress(&ptr, vb_logtab_global);
+    return static_cast<const double2 *>(ptr);
+}
+
 cudaError_t vb_init_tables()
 {
     if (g_tables_ready) return cudaSuccess;

@@ -83,6 +83,24 @@ cudaError_t vb_launch_scale_system(double *G, int T, long long cols, const doubl
 cudaError_t vb_launch_gram_panel(const VbGramProblem &prob, long long row0, int nchunk, int T,
                                  double *panel, double *stats, cudaStream_t stream);
 
+cudaError_t vb_launch_sqrt(const double *w, long long n, double *out, cudaStream_t stream);
+
+// Fused in-shared-memory Gram variant (vb_gemm.cu): the Jacobian rows are GENERATED into the
+// DMMA operand stages by four generator warps instead of being streamed from a panel.
+struct VbFusedGramParams {
+    const double *east, *north;  // n data coordinates
+    const double *sqrt_w;        // n, or null
+    long long n;
+    const double *fe, *fn;       // m force coordinates
+    long long m;
+    double mindist;
+    double *c_base;
+    int T;
+    int accumulate;
+    int strip;
+};
+cudaError_t vb_launch_fused_gram(const VbFusedGramParams &p, cudaStream_t stream);
+
 // Cholesky and solves on tile-packed storage (vb_chol.cu)
 cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream);
 cudaError_t vb_solve_tiled(const double *L, int T, double *x, cudaStream_t stream);
