@@ -64,6 +64,19 @@ def test_fused_in_smem_gram_matches_staged(env, mindist, weighted):
     assert np.max(np.abs(f1 - f0)) <= 1e-6 * np.max(np.abs(f0))
 
 
+def test_single_launch_sweeps_match_per_block_kernels(env):
+    vb, kernels, lib = env
+    e, nn, d = sample(2100, seed=7)
+    forces = []
+    try:
+        for variant in (1, 0):
+            assert lib.vb200_set_option(b"solve_variant", float(variant)) == 0
+            forces.append(kernels.fit_spline(e, nn, d, None, e, nn, 0.0, 1e-2))
+    finally:
+        lib.vb200_set_option(b"solve_variant", 1.0)
+    assert np.max(np.abs(forces[1] - forces[0])) <= 1e-6 * np.max(np.abs(forces[0]))
+
+
 def test_chol_panel_width_does_not_change_the_solution(env):
     vb, kernels, lib = env
     e, nn, d = sample(1500, seed=5)
@@ -75,4 +88,5 @@ def test_chol_panel_width_does_not_change_the_solution(env):
     finally:
         lib.vb200_set_option(b"chol_panel_tiles", 8.0)
     for f in forces[1:]:
-        assert np.max(np.abs(f - forces[0])) <= 1e-8 * np.max(np.abs(forces[0]))
+        # different panel widths reorder the trailing updates: agreement to ~cond*eps (cond ~ 3e9 here)
+        assert np.max(np.abs(f - forces[0])) <= 1e-6 * np.max(np.abs(forces[0]))

@@ -298,6 +298,7 @@ int vb200_set_option(const char *key, double value)
     if (k == "predict_exact") g_opt.predict_exact = value != 0.0;
     else if (k == "chol_panel_tiles") g_opt.chol_panel_tiles = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "gram_slab_chunks") g_opt.gram_slab_chunks = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
+    else if (k == "solve_variant") vb_solve_variant = (int)value;
     else if (k == "gram_fused") g_opt.gram_fused = value != 0.0;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
@@ -620,7 +621,9 @@ int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, in
     CU(vb_cholesky_tiled(L, T, g_opt.chol_panel_tiles, d_info, st));
     CU(cudaEventRecord(fac.b, st));
     CU(span_begin(&sol, st));
-    CU(vb_solve_tiled(L, T, rhs, st));
+    int *d_flags;
+    CU(ws_get("sweep_flags", sizeof(int) * 2 * T, (void **)&d_flags));
+    CU(vb_solve_tiled(L, T, rhs, d_flags, st));
     vb_unscale_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(rhs, inv_scale, cols, ob.dev);
     vb_diag_minmax_kernel<<<1, 256, 0, st>>>(L, T, cols, mm);
     vb_launch_counter += 2;

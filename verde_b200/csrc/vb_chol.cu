@@ -211,6 +211,126 @@ vb_bwd_update_kernel(const double *__restrict__ Lmat, int T, int k, double *__re
     }
 }
 
+// ---- single-launch triangular sweeps ------------------------------------------------------
+// The per-block-row kernels above cost two launches and ~20 us of latency per block row
+// (18 ms per sweep at T = 391).  vb_trisweep_kernel does a whole sweep in ONE cooperative
+// launch: CTA c owns block rows c, c+G, ... (descending for the backward sweep); for a row it
+// streams the row's off-diagonal tiles into REGISTERS before it needs the matching solution
+// block (128 KB in flight per CTA -> HBM-bound, not latency-bound), waits on a per-block flag
+// published by the CTA that solved that block, accumulates, then solves its diagonal tile from
+// shared memory and publishes.  Co-residency is guaranteed by the cooperative launch, and a CTA
+// only ever waits for lower-numbered (forward) / higher-numbered (backward) blocks, which are
+// always ahead of it, so the flags cannot deadlock.
+constexpr int SWEEP_THREADS = 256;
+
+__device__ __forceinline__ void flag_wait(const int *flag)
+{
+    int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    } while (v == 0);
+}
+__device__ __forceinline__ void flag_set(int *flag)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags)
+{
+    extern __shared__ __align__(16) double sm[];
+    double *st = sm;                                    // diagonal tile: fwd [c*128 + r], bwd [r*129 + c]
+    double *sv = sm + VB_TILE * (VB_TILE + 1);          // solution block of the tile being applied
+    double *sacc = sv + VB_TILE;                        // 2 x 128 partial sums
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int it = blockIdx.x; it < T; it += gridDim.x) {
+        const int i = BACKWARD ? T - 1 - it : it;
+        // stage the diagonal tile (needed last) while the off-diagonal stream runs
+        const double *dtile = Lmat + vb_tile_index(i, i, T) * VB_TILE_ELEMS;
+        if (!BACKWARD) {
+            for (int idx = tid; idx < VB_TILE_ELEMS / 2; idx += SWEEP_THREADS)
+                reinterpret_cast<double2 *>(st)[idx] = reinterpret_cast<const double2 *>(dtile)[idx];
+        } else {
+            for (int idx = tid; idx < VB_TILE_ELEMS; idx += SWEEP_THREADS) {
+                const int c = idx >> 7, r = idx & 127;
+                st[r * (VB_TILE + 1) + c] = dtile[idx];
+            }
+        }
+        if (!BACKWARD) {
+            // y_i = L_ii^{-1} (b_i - sum_{k<i} L(i,k) y_k): thread (r, h) covers columns c = 2j + h
+            const int r = tid & 127, h = tid >> 7;
+            double acc = 0.0;
+            for (int k = 0; k < i; ++k) {
+                const double *tile = Lmat + vb_tile_index(i, k, T) * VB_TILE_ELEMS;
+                double l[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) l[j] = __ldcs(tile + (2 * j + h) * VB_TILE + r);
+                if (tid == 0) flag_wait(flags + k);
+                __syncthreads();
+                if (tid < VB_TILE) sv[tid] = __ldcg(x + k * VB_TILE + tid);
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) acc = fma(l[j], sv[2 * j + h], acc);
+            }
+            sacc[tid] = acc;
+            __syncthreads();
+            double v = 0.0;
+            if (tid < VB_TILE) v = x[i * VB_TILE + tid] - (sacc[tid] + sacc[tid + VB_TILE]);
+            for (int c = 0; c < VB_TILE; ++c) {
+                if (tid == c) sv[c] = v / st[c * VB_TILE + c];
+                __syncthreads();
+                if (tid > c && tid < VB_TILE) v = fma(-st[c * VB_TILE + tid], sv[c], v);
+            }
+            if (tid < VB_TILE) x[i * VB_TILE + tid] = sv[tid];
+        } else {
+            // x_i = L_ii^{-T} (y_i - sum_{k>i} L(k,i)^T x_k): warp w covers columns 16w..16w+15, lanes run along rows
+            double acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.0;
+            for (int k = T - 1; k > i; --k) {
+                const double *tile = Lmat + vb_tile_index(k, i, T) * VB_TILE_ELEMS;
+                double l[64];
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) l[c * 4 + q] = __ldcs(tile + (warp * 16 + c) * VB_TILE + lane + 32 * q);
+                if (tid == 0) flag_wait(flags + k);
+                __syncthreads();
+                if (tid < VB_TILE) sv[tid] = __ldcg(x + k * VB_TILE + tid);
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[c] = fma(l[c * 4 + q], sv[lane + 32 * q], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double v = acc[c];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) sacc[warp * 16 + c] = v;
+            }
+            __syncthreads();
+            double v = 0.0;
+            if (tid < VB_TILE) v = x[i * VB_TILE + tid] - sacc[tid];
+            for (int c = VB_TILE - 1; c >= 0; --c) {
+                if (tid == c) sv[c] = v / st[c * (VB_TILE + 1) + c];
+                __syncthreads();
+                if (tid < c) v = fma(-st[c * (VB_TILE + 1) + tid], sv[c], v);
+            }
+            if (tid < VB_TILE) x[i * VB_TILE + tid] = sv[tid];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            flag_set(flags + i);
+        }
+        __syncthreads();
+    }
+}
+
 long long col_base(int c, int T)
 {
     return ((long long)c * T - ((long long)c * (c - 1)) / 2 - c) * VB_TILE_ELEMS;
@@ -272,8 +392,35 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
 }
 
 // x (length T*128) is overwritten by the solution of L L^T x = b.
-cudaError_t vb_solve_tiled(const double *L, int T, double *x, cudaStream_t stream)
+int vb_solve_variant = 1;  // 1: one cooperative launch per sweep, 0: two launches per block row
+
+static cudaError_t solve_cooperative(const double *L, int T, double *x, int *flags, cudaStream_t stream)
 {
+    const int smem = (VB_TILE * (VB_TILE + 1) + VB_TILE + 2 * SWEEP_THREADS) * (int)sizeof(double);
+    cudaError_t err;
+    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+    if ((err = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev)) != cudaSuccess) return err;
+    if (!coop) return cudaErrorNotSupported;
+    if ((err = cudaFuncSetAttribute(vb_trisweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(vb_trisweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vb_trisweep_kernel<false>, SWEEP_THREADS, smem)) != cudaSuccess) return err;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int grid = T < sms ? T : sms;
+    if ((err = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * T, stream)) != cudaSuccess) return err;
+    int *fl_f = flags, *fl_b = flags + T;
+    void *args_f[] = {(void *)&L, (void *)&T, (void *)&x, (void *)&fl_f};
+    void *args_b[] = {(void *)&L, (void *)&T, (void *)&x, (void *)&fl_b};
+    if ((err = cudaLaunchCooperativeKernel((void *)vb_trisweep_kernel<false>, dim3(grid), dim3(SWEEP_THREADS), args_f, smem, stream)) != cudaSuccess) return err;
+    if ((err = cudaLaunchCooperativeKernel((void *)vb_trisweep_kernel<true>, dim3(grid), dim3(SWEEP_THREADS), args_b, smem, stream)) != cudaSuccess) return err;
+    vb_launch_counter += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream)
+{
+    if (vb_solve_variant == 1 && flags != nullptr) return solve_cooperative(L, T, x, flags, stream);
     const int fwd_smem = VB_TILE_ELEMS * (int)sizeof(double);
     const int bwd_smem = VB_TILE * (VB_TILE + 1) * (int)sizeof(double);
     cudaError_t err;

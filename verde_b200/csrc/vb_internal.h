@@ -103,4 +103,6 @@ cudaError_t vb_launch_fused_gram(const VbFusedGramParams &p, cudaStream_t stream
 
 // Cholesky and solves on tile-packed storage (vb_chol.cu)
 cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream);
-cudaError_t vb_solve_tiled(const double *L, int T, double *x, cudaStream_t stream);
+// flags: 2*T ints of device scratch for the single-launch sweeps (null -> per-block-row kernels)
+cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream);
+extern int vb_solve_variant;
