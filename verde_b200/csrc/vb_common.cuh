@@ -81,23 +81,29 @@ __device__ __forceinline__ void vb_greens2d_exact(double dx, double dy, double m
 // a degree-4 polynomial (truncation r^5/5 <= 2^-57 absolute).
 #define VB_LOGTAB_SMEM_DOUBLES (VB_LOGTAB_ENTRIES * 2)
 
-// gtab: global copy of the table (filled by vb_init_tables()).
+// gtab: global copy of the table (filled by vb_init_tables()).  REP > 1 interleaves REP copies
+// (entry idx, copy r at double2 index idx*REP + r); lane l reads copy l % REP, which spreads the
+// 8 lanes of a quarter-warp over more bank groups (REP = 4: ~1.5-way instead of ~2.5-way conflicts).
+template <int REP = 1>
 __device__ __forceinline__ void vb_logtab_stage(double *smem_tab, const double2 *gtab)
 {
     // called by all threads of a CTA; caller syncs afterwards
-    for (int t = threadIdx.x; t < VB_LOGTAB_ENTRIES; t += blockDim.x)
-        reinterpret_cast<double2 *>(smem_tab)[t] = gtab[t];
+    for (int t = threadIdx.x; t < VB_LOGTAB_ENTRIES * REP; t += blockDim.x)
+        reinterpret_cast<double2 *>(smem_tab)[t] = gtab[t / REP];
 }
 
 // log(d) for normal positive d; `tab` is the shared-memory table.  Never produces inf/NaN:
 // d = 0 reads as 2^-1023 (finite log), so r2 * log(r2) is an exact 0 at r2 = 0.
 // 8 FP64 issue slots: 1 (exponent) + 1 (r) + 2 (Horner) + 1 (r^2) + 1 + 2 (assembly).
+template <int REP = 1>
 __device__ __forceinline__ double vb_log_fast(double d, const double2 *tab)
 {
+    static_assert(REP == 1 || REP == 2 || REP == 4, "replication factor");
     const int hi = __double2hiint(d);
     const int lo = __double2loint(d);
-    // byte offset of table entry idx = mantissa bits 19..10: idx * 16
-    const int off = (hi >> 6) & 0x3FF0;
+    // byte offset of table entry idx = mantissa bits 19..10: idx * 16 * REP (tab already points at
+    // this lane's copy)
+    const int off = REP == 1 ? ((hi >> 6) & 0x3FF0) : REP == 2 ? ((hi >> 5) & 0x7FE0) : ((hi >> 4) & 0xFFC0);
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // double(biased exponent - 1023) without an I2F: 2^52 + biased as a bit pattern
     const double ed = __hiloint2double(0x43300000, (unsigned)hi >> 20) - 4503599627371519.0;
@@ -142,18 +148,18 @@ __device__ __forceinline__ double vb_rcp_fast(double x)
 //   (15 FP64 slots per pair); HAS_MINDIST = true adds 1e-300 to r2 inside the FMA chain so the
 //   rsqrt seed never sees 0 (sqrt -> 1e-150, absorbed by any mindist > 1e-134): 22 slots.
 #define VB_R2_FLOOR 1e-300
-template <bool HAS_MINDIST>
+template <bool HAS_MINDIST, int REP = 1>
 __device__ __forceinline__ double vb_greens_fast(double dx, double dy, double mindist,
                                                  const double2 *tab)
 {
     if (HAS_MINDIST) {
         const double r2 = fma(dx, dx, fma(dy, dy, VB_R2_FLOOR));
         const double d = vb_sqrt_fast(r2) + mindist;
-        const double lg = vb_log_fast(d, tab);
+        const double lg = vb_log_fast<REP>(d, tab);
         return (d * d) * (lg - 1.0);
     } else {
         const double r2 = fma(dx, dx, dy * dy);
-        const double lg = vb_log_fast(r2, tab);
+        const double lg = vb_log_fast<REP>(r2, tab);
         return r2 * fma(0.5, lg, -1.0);
     }
 }

@@ -57,6 +57,8 @@ vb_jacobian2d_kernel(const double *__restrict__ east, const double *__restrict__
 constexpr int PRED_THREADS = 256;
 constexpr int PRED_WARPS = PRED_THREADS / 32;
 constexpr int PRED_CHUNK = 1024;  // forces staged per pass: 3 * 8 KB
+constexpr int PRED_TAB_REP = 4;    // copies of the log table in the scalar kernel's dynamic smem
+constexpr int PRED_TAB_BYTES = VB_LOGTAB_ENTRIES * 16 * PRED_TAB_REP;
 constexpr int PRED2_CHUNK = 512;  // 2-D kernel stages 4 arrays; static smem limit is 48 KB
 
 // MODE 0: fast Green's, mindist == 0; MODE 1: fast, mindist != 0; MODE 2: exact.
@@ -67,13 +69,13 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
                   const double *__restrict__ force, int m_begin_stride, int m_total,
                   double mindist, double *__restrict__ out)
 {
-    __shared__ __align__(16) double s_tab[MODE == 2 ? 2 : VB_LOGTAB_SMEM_DOUBLES];
+    extern __shared__ __align__(16) double s_tab[];  // PRED_TAB_REP interleaved copies of the log table
     __shared__ double s_fe[PRED_CHUNK], s_fn[PRED_CHUNK], s_f[PRED_CHUNK];
     __shared__ double s_out[PRED_WARPS * PTS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (MODE != 2) vb_logtab_stage(s_tab, vb_logtab_global);
-    const double2 *tab = reinterpret_cast<const double2 *>(s_tab);
+    if (MODE != 2) vb_logtab_stage<PRED_TAB_REP>(s_tab, vb_logtab_global);
+    const double2 *tab = reinterpret_cast<const double2 *>(s_tab) + (lane & (PRED_TAB_REP - 1));
 
     // force range of this split (blockIdx.y): [m0, m1)
     const int m0 = min(m_total, (int)blockIdx.y * m_begin_stride);
@@ -111,8 +113,8 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
 #pragma unroll
             for (int p = 0; p < PTS; ++p) {
                 double g;
-                if (MODE == 0) g = vb_greens_fast<false>(px[p] - fx, py[p] - fy, mindist, tab);
-                else if (MODE == 1) g = vb_greens_fast<true>(px[p] - fx, py[p] - fy, mindist, tab);
+                if (MODE == 0) g = vb_greens_fast<false, PRED_TAB_REP>(px[p] - fx, py[p] - fy, mindist, tab);
+                else if (MODE == 1) g = vb_greens_fast<true, PRED_TAB_REP>(px[p] - fx, py[p] - fy, mindist, tab);
                 else g = vb_greens_exact(px[p] - fx, py[p] - fy, mindist);
                 acc[p] = fma(g, fc, acc[p]);
             }
@@ -308,12 +310,18 @@ static cudaError_t launch_predict_pts_minb(int mode, dim3 grid, const double *e,
                                            const double *f, int stride, int m, double mindist,
                                            double *out, cudaStream_t stream)
 {
-    if (mode == 0)
-        vb_predict_kernel<PTS, 0, MINB><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
-    else if (mode == 1)
-        vb_predict_kernel<PTS, 1, MINB><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
-    else
-        vb_predict_kernel<PTS, 2, 2><<<grid, PRED_THREADS, 0, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    cudaError_t err;
+    if (mode == 0) {
+        err = cudaFuncSetAttribute(vb_predict_kernel<PTS, 0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_TAB_BYTES);
+        if (err != cudaSuccess) return err;
+        vb_predict_kernel<PTS, 0, MINB><<<grid, PRED_THREADS, PRED_TAB_BYTES, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    } else if (mode == 1) {
+        err = cudaFuncSetAttribute(vb_predict_kernel<PTS, 1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_TAB_BYTES);
+        if (err != cudaSuccess) return err;
+        vb_predict_kernel<PTS, 1, MINB><<<grid, PRED_THREADS, PRED_TAB_BYTES, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    } else {
+        vb_predict_kernel<PTS, 2, 2><<<grid, PRED_THREADS, 16, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, out);
+    }
     return cudaGetLastError();
 }
 
