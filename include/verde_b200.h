@@ -130,6 +130,24 @@ int vb200_gram_accumulate(int kind, const double *east, const double *north, con
 int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
                      double damping, int keep_gram, double *out_params, vb200_fit_info *info);
 
+/* ---- factor once, solve many right-hand sides (Vector of Splines on shared coordinates) ------
+ * factor:  like vb200_gram_solve but stops after the Cholesky factorisation: gram_dev is overwritten
+ *          by L (tile-packed) and inv_scale_dev (DEVICE, vb200_padded_cols(cols) doubles) receives
+ *          the column scaling 1/s_j.
+ * solve:   out_params = D L^-T L^-1 D rhs for one UNSCALED right-hand side rhs = J^T W d
+ *          (length cols, host or device).
+ * jacobian_transpose_apply: out[j] = sum_i g(e_i - fe_j, n_i - fn_j) v[i], i.e. J^T v for the
+ *          scalar spline without forming J (v = W d gives the right-hand side of another data
+ *          component on the same coordinates). */
+int64_t vb200_padded_cols(int64_t cols);
+int vb200_gram_factor(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
+                      double damping, double *inv_scale_dev, vb200_fit_info *info);
+int vb200_chol_solve(const double *chol_dev, const double *inv_scale_dev, int64_t cols,
+                     const double *rhs, double *out_params, vb200_fit_info *info);
+int vb200_jacobian_transpose_apply(const double *east, const double *north, int64_t n,
+                                   const double *force_east, const double *force_north, int64_t m,
+                                   double mindist, const double *v, double *out);
+
 /* ---- least squares on an explicit Jacobian ----------------------------------------------
  * replaces verde/base/least_squares.py:17 least_squares(jacobian, data, weights, damping):
  * jac row-major (n, m); damped branch only (damping > 0). */

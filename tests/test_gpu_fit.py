@@ -251,3 +251,41 @@ def test_gridder_api_surface(vb, golden_spline):
     assert list(table.columns) == ["northing", "easting", "scalars"]
     prof = sp.profile((0, -5000), (5000, 0), 33)
     assert list(prof.columns) == ["northing", "easting", "distance", "scalars"] and len(prof) == 33
+
+
+def test_vector_of_splines_shares_one_factorisation(vb, golden_spline):
+    """
+    SURVEY 8f rank 1: Vector([Spline, Spline]) on shared coordinates builds ONE Gram matrix and ONE
+    Cholesky factor; every component must match an independent fit of that component.
+    """
+    g = golden_spline
+    e, n, d = g["east"], g["north"], g["data"]
+    d2 = np.cos(e / 700.0) * 300.0 + n * 0.05
+    w = g["weights"]
+    for weights in (None, (w, w)):
+        vec = vb.Vector([vb.Spline(damping=1e-4), vb.Spline(damping=1e-4)]).fit((e, n), (d, d2), weights=weights)
+        assert vec.components[0].fit_info_["gemm_launches"] >= 1
+        for comp, data, wk in zip(vec.components, (d, d2), (None, None) if weights is None else weights):
+            alone = vb.Spline(damping=1e-4).fit((e, n), data, weights=wk)
+            assert np.max(np.abs(comp.force_ - alone.force_)) <= 1e-5 * np.max(np.abs(alone.force_))
+            grid = (g["grid_east"], g["grid_north"])
+            assert np.max(np.abs(comp.predict(grid) - alone.predict(grid))) <= 1e-7 * np.ptp(data)
+        pe, pn = vec.predict((e, n))
+        assert pe.shape == e.shape and pn.shape == e.shape
+    # the reference result for component 0 with weights (golden d1em4_w)
+    ref = g["force_d1em4_w"]
+    assert np.max(np.abs(vec.components[0].force_ - ref)) <= force_tol(float(g["cond_d1em4_w"])) * np.max(np.abs(ref))
+    # different dampings -> falls back to independent fits, same API
+    mixed = vb.Vector([vb.Spline(damping=1e-4), vb.Spline(damping=1e-2)]).fit((e, n), (d, d2))
+    assert mixed.components[1].damping == 1e-2 and mixed.components[1].force_.shape == e.shape
+
+
+def test_chain_of_splines(vb, golden_spline):
+    g = golden_spline
+    e, n, d = g["east"], g["north"], g["data"]
+    chain = vb.Chain([("smooth", vb.Spline(damping=1e-1)), ("detail", vb.Spline(damping=1e-5))]).fit((e, n), d)
+    first = vb.Spline(damping=1e-1).fit((e, n), d)
+    second = vb.Spline(damping=1e-5).fit((e, n), d - first.predict((e, n)))
+    np.testing.assert_allclose(chain.predict((e, n)), first.predict((e, n)) + second.predict((e, n)), rtol=0,
+                               atol=1e-9 * np.ptp(d))
+    assert set(chain.named_steps) == {"smooth", "detail"}

@@ -6,10 +6,13 @@ verde/chain.py:17-138).  Pure host glue: they only ever call ``fit`` /
 ``filter`` / ``predict`` on their members, so the B200 gridders slot in
 unchanged.
 """
+import numpy as np
 from sklearn.utils.validation import check_is_fitted
 
-from .base import BaseGridder, check_data, check_fit_input
+from . import dist, kernels
+from .base import BaseGridder, check_data, check_fit_input, n_1d_arrays
 from .coords import get_region
+from .scalar_spline import Spline, parse_engine
 
 
 class Vector(BaseGridder):
@@ -31,9 +34,58 @@ class Vector(BaseGridder):
             raise ValueError("Weights must be a tuple of arrays. {} given.".format(type(weights)))
         coordinates, data, weights = check_fit_input(coordinates, data, weights)
         self.region_ = get_region(coordinates[:2])
-        for estimator, data_comp, weight_comp in zip(self.components, data, weights):
-            estimator.fit(coordinates, data_comp, weight_comp)
+        if self._splines_share_a_system(data, weights):
+            self._fit_shared(coordinates, data, weights)
+        else:
+            for estimator, data_comp, weight_comp in zip(self.components, data, weights):
+                estimator.fit(coordinates, data_comp, weight_comp)
         return self
+
+    def _splines_share_a_system(self, data, weights):
+        """
+        True when every component is a damped :class:`Spline` with the same parameters and the
+        same (or no) weights: then all components have the SAME Jacobian and normal matrix and only
+        the right-hand sides differ, so one Gram accumulation + one Cholesky serves them all.
+        """
+        comps = self.components
+        if not isinstance(data, tuple) or len(comps) < 2 or len(comps) != len(data) or dist.sharding_active():
+            return False
+        first = comps[0]
+        if any(type(c) is not Spline for c in comps) or first.damping is None:
+            return False
+        if any(c.damping != first.damping or c.mindist != first.mindist or c.engine != first.engine
+               or c.force_coords is not first.force_coords for c in comps[1:]):
+            return False
+        if all(w is None for w in weights):
+            return True
+        return all(w is not None and np.array_equal(w, weights[0]) for w in weights)
+
+    def _fit_shared(self, coordinates, data, weights):
+        first = self.components[0]
+        parse_engine(first.engine)
+        east, north = n_1d_arrays(coordinates, n=2)
+        if first.force_coords is None:
+            force_coords = tuple(i.copy() for i in (east, north))
+        else:
+            force_coords = first.force_coords
+        force_east, force_north = n_1d_arrays(force_coords, n=2)
+        w = weights[0]
+        kernels._warn_underdetermined(east.size, force_east.size)
+        system = kernels.GramSystem(force_east.size)
+        system.accumulate(0, east, north, data[0], w, force_east, force_north, first.mindist)
+        system.factor(east.size, first.damping)
+        region = get_region(coordinates[:2])
+        for k, (estimator, data_comp) in enumerate(zip(self.components, data)):
+            if k == 0:
+                rhs = system.rhs()
+            else:
+                v = np.ravel(data_comp) if w is None else np.ravel(w) * np.ravel(data_comp)
+                rhs = kernels.jacobian_transpose_apply(east, north, force_east, force_north, first.mindist, v)
+            estimator.force_ = system.solve_rhs(rhs)
+            estimator.region_ = region
+            estimator.force_coords_ = (force_coords if first.force_coords is not None
+                                       else tuple(i.copy() for i in force_coords))
+            estimator.fit_info_ = dict(kernels.LAST_FIT_INFO)
 
     def predict(self, coordinates):
         check_is_fitted(self, ["region_"])

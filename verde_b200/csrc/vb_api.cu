@@ -652,6 +652,129 @@ int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, in
     return 0;
 }
 
+int64_t vb200_padded_cols(int64_t cols) { return (cols + VB_TILE - 1) / VB_TILE * VB_TILE; }
+
+int vb200_gram_factor(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
+                      double damping, double *inv_scale_dev, vb200_fit_info *info)
+{
+    if (cols <= 0 || total_rows <= 0) return fail(VB200_E_BADARG, "bad sizes");
+    if (!gram_dev || !stats_dev || !inv_scale_dev) return fail(VB200_E_BADARG, "null pointer");
+    if (!(damping > 0.0)) return fail(VB200_E_BADARG, "damping must be > 0 (the damping=None branch of the reference is out of scope)");
+    if (!is_device_ptr(gram_dev) || !is_device_ptr(stats_dev) || !is_device_ptr(inv_scale_dev))
+        return fail(VB200_E_BADARG, "gram/stats/inv_scale buffers must be device memory");
+    cudaStream_t st = 0;
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    double *rhs, *mm;
+    int *d_info;
+    CU(ws_get("rhs", sizeof(double) * Mpad, (void **)&rhs));
+    CU(ws_get("minmax", sizeof(double) * 2, (void **)&mm));
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    if (info) {
+        info->block_rows = T;
+        info->cols = cols;
+        if (info->rows == 0) info->rows = total_rows;
+    }
+    prof_reset();
+    const long long launches0 = vb_launch_counter;
+    Span fac;
+    CU(span_begin(&fac, st));
+    CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale_dev, rhs, st));
+    CU(vb_launch_scale_system(gram_dev, T, cols, inv_scale_dev, damping, st));
+    CU(vb_cholesky_tiled(gram_dev, T, g_opt.chol_panel_tiles, d_info, st));
+    vb_diag_minmax_kernel<<<1, 256, 0, st>>>(gram_dev, T, cols, mm);
+    ++vb_launch_counter;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(fac.b, st));
+    int h_info = 0;
+    double h_mm[2] = {0, 0};
+    CU(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double fms = span_ms(fac);
+    if (info) {
+        info->factor_ms += fms;
+        info->info = h_info;
+        info->diag_min = h_mm[0];
+        info->diag_max = h_mm[1];
+        info->kernel_launches += vb_launch_counter - launches0;
+    }
+    prof_collect(info);
+    if (h_info > 0) {
+        fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
+        return h_info;
+    }
+    return 0;
+}
+
+int vb200_chol_solve(const double *chol_dev, const double *inv_scale_dev, int64_t cols, const double *rhs,
+                     double *out_params, vb200_fit_info *info)
+{
+    if (cols <= 0) return fail(VB200_E_BADARG, "bad sizes");
+    if (!chol_dev || !inv_scale_dev || !rhs || !out_params) return fail(VB200_E_BADARG, "null pointer");
+    if (!is_device_ptr(chol_dev) || !is_device_ptr(inv_scale_dev))
+        return fail(VB200_E_BADARG, "factor / inv_scale buffers must be device memory");
+    cudaStream_t st = 0;
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    const double *drhs;
+    CU(stage_in("in_rhs", rhs, cols, &drhs, st));
+    double *x;
+    int *d_flags;
+    CU(ws_get("rhs", sizeof(double) * Mpad, (void **)&x));
+    CU(ws_get("sweep_flags", sizeof(int) * 2 * T, (void **)&d_flags));
+    OutBuf ob;
+    CU(stage_out("out_params", out_params, cols, &ob));
+    const long long launches0 = vb_launch_counter;
+    Span sol;
+    CU(span_begin(&sol, st));
+    CU(cudaMemsetAsync(x, 0, sizeof(double) * Mpad, st));
+    vb_unscale_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(drhs, inv_scale_dev, cols, x);  // D rhs
+    CU(vb_solve_tiled(chol_dev, T, x, d_flags, st));
+    vb_unscale_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(x, inv_scale_dev, cols, ob.dev);  // D c
+    vb_launch_counter += 2;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(sol.b, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    const double sms = span_ms(sol);
+    if (info) {
+        info->solve_ms += sms;
+        info->kernel_launches += vb_launch_counter - launches0;
+    }
+    return 0;
+}
+
+int vb200_jacobian_transpose_apply(const double *east, const double *north, int64_t n,
+                                   const double *force_east, const double *force_north, int64_t m,
+                                   double mindist, const double *v, double *out)
+{
+    if (n < 0 || m < 0) return fail(VB200_E_BADARG, "negative size");
+    if (m == 0) return 0;
+    if (!force_east || !force_north || !out || (n > 0 && (!east || !north || !v)))
+        return fail(VB200_E_BADARG, "null pointer");
+    if (n > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many data points");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dfe, *dfn, *dv;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("in_fe", force_east, m, &dfe, st));
+    CU(stage_in("in_fn", force_north, m, &dfn, st));
+    CU(stage_in("in_f", v, n, &dv, st));
+    OutBuf ob;
+    CU(stage_out("out_pred", out, m, &ob));
+    // (J^T v)_j = sum_i g(e_i - fe_j, n_i - fn_j) v_i: the predict kernel with the roles of points and
+    // forces swapped (g is even), with the exact, reference-ordered Green's function
+    int pts, nsplit;
+    vb_predict_plan(m, n, &pts, &nsplit);
+    double *scratch = nullptr;
+    if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * nsplit * m, (void **)&scratch));
+    CU(vb_launch_predict(dfe, dfn, m, de, dn, dv, n, mindist, 1, pts, nsplit, scratch, ob.dev, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 static int fit_impl(int kind, const double *jac, const double *east, const double *north,
                     const double *data, const double *weights, int64_t n, const double *force_east,
                     const double *force_north, int64_t m, double mindist, double poisson,

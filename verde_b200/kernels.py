@@ -227,6 +227,48 @@ class GramSystem:
         return params
 
 
+    def factor(self, total_rows, damping):
+        "Scale, damp and factor in place (the Gram matrix becomes L); keeps 1/s for later solves."
+        _require_damping(damping)
+        self.inv_scale = self._torch.empty(self._lib.vb200_padded_cols(self.cols), dtype=self._torch.float64,
+                                           device=self.gram.device)
+        self._torch.cuda.synchronize()
+        rc = self._lib.vb200_gram_factor(_cabi.ptr(self.gram), _cabi.ptr(self.stats), self.cols, int(total_rows),
+                                         float(damping), _cabi.ptr(self.inv_scale), ctypes.byref(self.info))
+        _remember(self.info)
+        _cabi.check(rc, "gram_factor")
+        return self
+
+    def rhs(self):
+        "Device view of J^T W d of the data passed to ``accumulate`` (unscaled)."
+        return self.stats[: self.cols]
+
+    def solve_rhs(self, rhs):
+        "Parameters for one unscaled right-hand side J^T W d (numpy array or CUDA tensor); needs ``factor``."
+        if not hasattr(rhs, "data_ptr"):
+            rhs = _cabi.f64(rhs)
+        params = np.empty(self.cols, dtype=np.float64)
+        self._torch.cuda.synchronize()
+        rc = self._lib.vb200_chol_solve(_cabi.ptr(self.gram), _cabi.ptr(self.inv_scale), self.cols, _cabi.ptr(rhs),
+                                        _cabi.ptr(params), ctypes.byref(self.info))
+        _remember(self.info)
+        _cabi.check(rc, "chol_solve")
+        return params
+
+
+def jacobian_transpose_apply(east, north, force_east, force_north, mindist, v):
+    "J^T v for the scalar spline without forming J (exact Green's function)."
+    lib = _cabi.require_device()
+    e, n, fe, fn, vv = (_cabi.f64(a) for a in (east, north, force_east, force_north, v))
+    if vv.size != e.size:
+        raise ValueError("v must have one entry per data point")
+    out = np.empty(fe.size, dtype=np.float64)
+    _cabi.check(lib.vb200_jacobian_transpose_apply(_cabi.ptr(e), _cabi.ptr(n), e.size, _cabi.ptr(fe), _cabi.ptr(fn),
+                                                   fe.size, float(mindist), _cabi.ptr(vv), _cabi.ptr(out)),
+                "jacobian_transpose_apply")
+    return out
+
+
 def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindist, poisson, damping):
     """
     Row-sharded fit: every rank holds the full inputs, builds the normal
