@@ -19,6 +19,8 @@
  *  - return value: 0 = ok; > 0 = numerical failure (1-based index of the first
  *    non-positive Cholesky pivot, LAPACK `info` style); < 0 = VB200_E_* below.
  *    Nothing throws across the ABI.  vb200_last_error() gives a message.
+ *  - the library keeps per-process state (cached device workspace, options, last error per thread):
+ *    drive it from one host thread per process (the intended deployment is one process per GPU).
  *  - there is NO CPU fallback: without a CUDA device every compute entry point
  *    returns VB200_E_CUDA.
  */

@@ -57,7 +57,11 @@ std::map<std::string, Slot> g_ws;
 
 cudaError_t ws_get(const char *name, size_t bytes, void **out)
 {
-    Slot &s = g_ws[name];
+    // slots are per device: a process that switches devices must not see another device's pointers
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return de;
+    Slot &s = g_ws[std::to_string(dev) + ":" + name];
     if (s.bytes < bytes) {
         if (s.ptr) cudaFree(s.ptr);
         s.ptr = nullptr;
