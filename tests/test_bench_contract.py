@@ -1,0 +1,59 @@
+"""
+bench.py contract checks that need no GPU: the reference arm prints exactly one JSON line with the
+keys the driver reads, on the same metric / unit / config as the GPU arm.
+"""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def run_reference_arm(*extra):
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--cpu-sample", "1200", *extra]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [line for line in proc.stdout.splitlines() if line.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    import bench
+
+    line = run_reference_arm()
+    assert line["impl"] == "reference"
+    assert line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["dtype"] == "f64" and line["data"] == "synthetic"
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    cfg = line["config"]
+    assert "workload" in cfg and cfg["n_data"] == 50_000 and cfg["n_forces"] == 50_000 and cfg["grid_points"] == 4_000_000
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "n=m=1200" in cpu["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert proc.returncode == 0 and proc.stdout.strip() == ""
+
+
+def test_workload_generator_matches_checkerboard():
+    import numpy as np
+
+    import bench
+    import verde_b200 as vb
+
+    east, north, data, fe, fn, ge, gn = bench.make_workload(3000, 3000, (10, 12), True)
+    tab = vb.CheckerBoard().scatter(size=3000, random_state=0)
+    np.testing.assert_array_equal(east, tab.easting.values)
+    np.testing.assert_array_equal(north, tab.northing.values)
+    np.testing.assert_allclose(data, tab.scalars.values, rtol=1e-13, atol=1e-10)
+    assert fe is east and ge.size == 12 and gn.size == 10
