@@ -132,6 +132,17 @@ int vb200_gram_accumulate(int kind, const double *east, const double *north, con
 int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
                      double damping, int keep_gram, double *out_params, vb200_fit_info *info);
 
+/* solve_multi: SplineCV's damping sweep (verde/spline.py:243-255 refits every (mindist, damping, fold)
+ *         from scratch; the Gram matrix only depends on (mindist, fold)).  Scales G once, writes one
+ *         damped copy per damping and factors / solves all of them SIDE BY SIDE: every panel kernel
+ *         and every DMMA update launch covers the whole batch.  G is not modified.  dampings: HOST
+ *         array of n_dampings positive values; out_params: n_dampings x cols, row-major (host or
+ *         device); out_info (HOST, may be NULL): per-damping 0 or 1-based failed pivot.  As many
+ *         systems as fit in free device memory are batched at a time. */
+int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int64_t cols,
+                           int64_t total_rows, const double *dampings, int32_t n_dampings,
+                           double *out_params, int32_t *out_info, vb200_fit_info *info);
+
 /* ---- factor once, solve many right-hand sides (Vector of Splines on shared coordinates) ------
  * factor:  like vb200_gram_solve but stops after the Cholesky factorisation: gram_dev is overwritten
  *          by L (tile-packed) and inv_scale_dev (DEVICE, vb200_padded_cols(cols) doubles) receives

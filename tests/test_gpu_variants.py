@@ -90,3 +90,37 @@ def test_chol_panel_width_does_not_change_the_solution(env):
     for f in forces[1:]:
         # different panel widths reorder the trailing updates: agreement to ~cond*eps (cond ~ 3e9 here)
         assert np.max(np.abs(f - forces[0])) <= 1e-6 * np.max(np.abs(forces[0]))
+
+
+@pytest.mark.parametrize("n", [700, 2100])
+def test_batched_damping_sweep_equals_one_solve_per_damping(env, n):
+    """vb200_gram_solve_multi factors all dampings side by side (batched panel kernels, one DMMA launch per
+    update for the whole batch, one cooperative sweep): same arithmetic per system -> same bits."""
+    vb, kernels, lib = env
+    e, nn, d = sample(n, seed=11)
+    w = np.random.RandomState(3).uniform(0.5, 2, e.size)
+    dampings = [1e-6, 1e-4, 1e-3, 1e-2, 1e-1, 1.0, 10.0]
+    system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, w, e, nn, 1e-5)
+    gram_before = system.gram.clone()
+    batched = system.solve_multi(e.size, dampings)
+    assert batched.shape == (len(dampings), e.size)
+    assert bool((system.gram == gram_before).all()), "the sweep must leave the Gram matrix untouched"
+    for k, damping in enumerate(dampings):
+        single = system.solve(e.size, damping, keep=True)
+        np.testing.assert_array_equal(batched[k], single)
+    # the older tile kernels walk the batch matrix by matrix: same answer
+    try:
+        assert lib.vb200_set_option(b"gemm_variant", 1.0) == 0
+        v2 = system.solve_multi(e.size, dampings[:3])
+    finally:
+        lib.vb200_set_option(b"gemm_variant", 3.0)
+    assert np.max(np.abs(v2 - batched[:3])) <= 1e-9 * np.max(np.abs(batched[:3]))
+
+
+def test_batched_sweep_reports_a_non_positive_definite_member(env):
+    vb, kernels, lib = env
+    e, nn, d = sample(300, seed=12)
+    system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, None, e, nn, 0.0)
+    system.gram.mul_(-1.0)  # -G - tiny*I is negative definite, -G + huge*I is fine
+    with pytest.raises(np.linalg.LinAlgError):
+        system.solve_multi(e.size, [1e-30, 1e30])

@@ -4,7 +4,8 @@ mindist 1e-5): the CPU oracle (bit-exact restatement of the reference, tests/tes
 the GPU box's host cores (needs ~80 GB of RAM and ~10 min) and compared with the B200 path on the
 same inputs.  Prints one JSON object.   python tools/parity_full_config2.py [n]
 """
-import json, os, sys, time, warnings
+import faulthandler, json, os, sys, time, warnings
+faulthandler.enable()
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -56,6 +56,7 @@ if 5 in which:
     dampings = [1e-8, 1e-6, 1e-4, 1e-3, 1e-2, 1e-1]
     mindists = [0, 1e-5, 1e-3, 1e-1]
     cv = vb.SplineCV(dampings=dampings, mindists=mindists)
-    t_fit, _ = timed(lambda: cv.fit(coords, d), reps=1)
+    t_fit, _ = timed(lambda: cv.fit(coords, d), reps=2)
     print(json.dumps({"config": 5, "points": 20000, "combos": 24, "folds": 5, "fit_s": t_fit, "scores": list(map(float, cv.scores_)),
-                      "best": [float(cv.mindist_), float(cv.damping_)], "final_fit_info": cv.spline_.fit_info_}), flush=True)
+                      "best": [float(cv.mindist_), float(cv.damping_)], "sweep_info": cv.sweep_info_,
+                      "final_fit_info": cv.spline_.fit_info_}), flush=True)

@@ -172,7 +172,8 @@ cudaError_t timed_gemm(const VbGemmParams &p, cudaStream_t st)
     e = vb_launch_gemm(p, st);
     cudaEventRecord(s.b, st);
     g_prof.gemm.push_back(s);
-    g_prof.gemm_flops += 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
+    g_prof.gemm_flops += 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi) *
+                         (double)(p.batch > 1 ? p.batch : 1);
     g_prof.launches += 1;
     return e;
 }
@@ -201,6 +202,20 @@ __global__ void vb_unscale_kernel(const double *__restrict__ x, const double *__
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < cols) out[j] = x[j] * inv_scale[j];
+}
+
+// batched flavours for the damping sweep: grid.y = system
+__global__ void vb_replicate_kernel(const double *__restrict__ src, long long count, double *__restrict__ dst)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < count) dst[(long long)blockIdx.y * count + j] = src[j];
+}
+__global__ void vb_unscale_batched_kernel(const double *__restrict__ x, long long xstride,
+                                          const double *__restrict__ inv_scale, long long cols,
+                                          double *__restrict__ out)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < cols) out[(long long)blockIdx.y * cols + j] = x[(long long)blockIdx.y * xstride + j] * inv_scale[j];
 }
 
 // min / max of diag(L)^2 over the first `cols` unknowns (single CTA; T*128 values)
@@ -652,6 +667,105 @@ int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, in
     if (h_info > 0) {
         fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
         return h_info;
+    }
+    return 0;
+}
+
+int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
+                           const double *dampings, int32_t n_dampings, double *out_params, int32_t *out_info,
+                           vb200_fit_info *info)
+{
+    if (cols <= 0 || total_rows <= 0) return fail(VB200_E_BADARG, "bad sizes");
+    if (n_dampings <= 0) return fail(VB200_E_BADARG, "need at least one damping");
+    if (!gram_dev || !stats_dev || !dampings || !out_params) return fail(VB200_E_BADARG, "null pointer");
+    if (is_device_ptr(dampings)) return fail(VB200_E_BADARG, "dampings must be a host array");
+    for (int b = 0; b < n_dampings; ++b)
+        if (!(dampings[b] > 0.0)) return fail(VB200_E_BADARG, "damping must be > 0 (the damping=None branch of the reference is out of scope)");
+    if (!is_device_ptr(gram_dev) || !is_device_ptr(stats_dev))
+        return fail(VB200_E_BADARG, "gram/stats buffers must be device memory");
+    cudaStream_t st = 0;
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    const long long stride = vb200_gram_doubles(cols);
+    // how many factors fit side by side: leave the allocator 1 GB of slack
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    {
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        auto it = g_ws.find(std::to_string(dev) + ":chol_batch");
+        if (it != g_ws.end()) free_b += it->second.bytes;  // re-usable
+    }
+    long long group = (long long)((free_b > (1ull << 30) ? free_b - (1ull << 30) : 0) / (sizeof(double) * (size_t)stride));
+    if (group > n_dampings) group = n_dampings;
+    if (group > 64) group = 64;
+    if (group < 1) return fail(VB200_E_NOMEM, "not enough device memory for one %lld x %lld factor", (long long)cols, (long long)cols);
+    double *Lb, *inv_scale, *rhs, *xb, *damp_dev, *mm;
+    int *d_info, *d_flags;
+    CU(ws_get("chol_batch", sizeof(double) * (size_t)stride * group, (void **)&Lb));
+    CU(ws_get("inv_scale", sizeof(double) * Mpad, (void **)&inv_scale));
+    CU(ws_get("rhs", sizeof(double) * Mpad, (void **)&rhs));
+    CU(ws_get("rhs_batch", sizeof(double) * Mpad * group, (void **)&xb));
+    CU(ws_get("damp_batch", sizeof(double) * group, (void **)&damp_dev));
+    CU(ws_get("minmax", sizeof(double) * 2, (void **)&mm));
+    CU(ws_get("info_batch", sizeof(int) * group, (void **)&d_info));
+    CU(ws_get("sweep_flags_batch", sizeof(int) * 2 * T * group, (void **)&d_flags));
+    OutBuf ob;
+    CU(stage_out("out_params_batch", out_params, (long long)cols * n_dampings, &ob));
+    if (info) {
+        info->block_rows = T;
+        info->cols = cols;
+        if (info->rows == 0) info->rows = total_rows;
+    }
+    prof_reset();
+    const long long launches0 = vb_launch_counter;
+    std::vector<int> h_info(n_dampings, 0);
+    double fms = 0.0, sms = 0.0;
+    double h_mm[2] = {0, 0};
+    CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale, rhs, st));
+    for (int b0 = 0; b0 < n_dampings; b0 += (int)group) {
+        const int nb = (int)((n_dampings - b0 < group) ? (n_dampings - b0) : group);
+        Span fac, sol;
+        CU(cudaMemcpyAsync(damp_dev, dampings + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        CU(span_begin(&fac, st));
+        CU(vb_launch_scale_system_batched(gram_dev, T, cols, inv_scale, damp_dev, nb, Lb, stride, st));
+        CU(vb_cholesky_tiled(Lb, T, g_opt.chol_panel_tiles, d_info, st, nb, stride));
+        CU(cudaEventRecord(fac.b, st));
+        CU(span_begin(&sol, st));
+        vb_replicate_kernel<<<dim3((unsigned)((Mpad + 255) / 256), nb), 256, 0, st>>>(rhs, Mpad, xb);
+        ++vb_launch_counter;
+        CU(vb_solve_tiled(Lb, T, xb, d_flags, st, nb, stride));
+        vb_unscale_batched_kernel<<<dim3((unsigned)((cols + 255) / 256), nb), 256, 0, st>>>(xb, Mpad, inv_scale, cols,
+                                                                                            ob.dev + (long long)b0 * cols);
+        vb_diag_minmax_kernel<<<1, 256, 0, st>>>(Lb, T, cols, mm);  // first system of the group (smallest damping first in SplineCV)
+        vb_launch_counter += 2;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(sol.b, st));
+        CU(cudaMemcpyAsync(h_info.data() + b0, d_info, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+        if (b0 == 0) CU(cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        fms += span_ms(fac);
+        sms += span_ms(sol);
+    }
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    int first_bad = 0;
+    for (int b = 0; b < n_dampings; ++b) {
+        if (out_info) out_info[b] = h_info[b];
+        if (h_info[b] > 0 && first_bad == 0) first_bad = h_info[b];
+    }
+    if (info) {
+        info->factor_ms += fms;
+        info->solve_ms += sms;
+        info->info = first_bad;
+        info->diag_min = h_mm[0];
+        info->diag_max = h_mm[1];
+        info->kernel_launches += vb_launch_counter - launches0;
+    }
+    prof_collect(info);
+    if (first_bad > 0) {
+        fail(first_bad, "normal matrix not positive definite: pivot %d <= 0", first_bad);
+        return first_bad;
     }
     return 0;
 }

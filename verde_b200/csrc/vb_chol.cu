@@ -31,11 +31,13 @@ constexpr int POTRF_BLK = 16;
 // its left (16 independent FMAs per own-row load), then factored column by column with
 // one shared-memory publish + barrier per pivot and per column.
 __global__ void __launch_bounds__(POTRF_THREADS)
-vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info)
+vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info, long long stride)
 {
     extern __shared__ __align__(16) double s[];  // s[c * 128 + r]
     __shared__ double s_piv[POTRF_BLK];
     const int r = threadIdx.x;
+    tile += (long long)blockIdx.x * stride;  // one CTA per matrix of a batch
+    d_info += blockIdx.x;
     for (int idx = r; idx < VB_TILE_ELEMS / 2; idx += POTRF_THREADS)
         reinterpret_cast<double2 *>(s)[idx] = reinterpret_cast<const double2 *>(tile)[idx];
     __syncthreads();
@@ -87,10 +89,11 @@ constexpr int TRSM_THREADS = 128;
 constexpr int TRSM_BLK = 32;
 
 __global__ void __launch_bounds__(TRSM_THREADS)
-vb_trsm_tiles_kernel(double *__restrict__ Lmat, int T, int k)
+vb_trsm_tiles_kernel(double *__restrict__ Lmat, int T, int k, long long stride)
 {
     extern __shared__ __align__(16) double sL[];  // sL[c * 128 + r] = L_kk(r, c)
     __shared__ double s_inv[VB_TILE];
+    Lmat += (long long)blockIdx.y * stride;  // grid.y = matrix of a batch
     const double *diag = Lmat + vb_tile_index(k, k, T) * VB_TILE_ELEMS;
     double *tile = Lmat + vb_tile_index(k + 1 + blockIdx.x, k, T) * VB_TILE_ELEMS;
     const int r = threadIdx.x;
@@ -237,15 +240,21 @@ __device__ __forceinline__ void flag_set(int *flag)
 
 template <bool BACKWARD>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
-vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags)
+vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags, int batch, long long stride)
 {
     extern __shared__ __align__(16) double sm[];
+    // a batch of independent systems shares the launch: CTAs [b*G, (b+1)*G) sweep matrix b
+    const int G = gridDim.x / batch;
+    const int mat = blockIdx.x / G, cta = blockIdx.x - mat * G;
+    Lmat += (long long)mat * stride;
+    x += (long long)mat * T * VB_TILE;
+    flags += mat * T;
     double *st = sm;                                    // diagonal tile: fwd [c*128 + r], bwd [r*129 + c]
     double *sv = sm + VB_TILE * (VB_TILE + 1);          // solution block of the tile being applied
     double *sacc = sv + VB_TILE;                        // 2 x 128 partial sums
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int it = blockIdx.x; it < T; it += gridDim.x) {
+    for (int it = cta; it < T; it += G) {
         const int i = BACKWARD ? T - 1 - it : it;
         // stage the diagonal tile (needed last) while the off-diagonal stream runs
         const double *dtile = Lmat + vb_tile_index(i, i, T) * VB_TILE_ELEMS;
@@ -338,8 +347,10 @@ long long col_base(int c, int T)
 
 }  // namespace
 
-cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream)
+cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream, int batch,
+                              long long stride)
 {
+    if (batch < 1) batch = 1;
     cudaError_t err;
     const int potrf_smem = VB_TILE_ELEMS * (int)sizeof(double);
     const int trsm_smem = VB_TILE_ELEMS * (int)sizeof(double);
@@ -347,17 +358,17 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
     if ((err = cudaFuncSetAttribute(vb_trsm_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem)) != cudaSuccess) return err;
     if (panel_tiles < 1) panel_tiles = 1;
     if (panel_tiles > VB_MAX_KCHUNKS) panel_tiles = VB_MAX_KCHUNKS;
-    if ((err = cudaMemsetAsync(d_info, 0, sizeof(int), stream)) != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(d_info, 0, sizeof(int) * batch, stream)) != cudaSuccess) return err;
 
     for (int k0 = 0; k0 < T; k0 += panel_tiles) {
         const int pw = (T - k0 < panel_tiles) ? (T - k0) : panel_tiles;
         for (int kk = 0; kk < pw; ++kk) {
             const int k = k0 + kk;
-            vb_potrf_tile_kernel<<<1, POTRF_THREADS, potrf_smem, stream>>>(
-                L + vb_tile_index(k, k, T) * VB_TILE_ELEMS, k, d_info);
+            vb_potrf_tile_kernel<<<batch, POTRF_THREADS, potrf_smem, stream>>>(
+                L + vb_tile_index(k, k, T) * VB_TILE_ELEMS, k, d_info, stride);
             ++vb_launch_counter;
             if (k + 1 < T) {
-                vb_trsm_tiles_kernel<<<T - k - 1, TRSM_THREADS, trsm_smem, stream>>>(L, T, k);
+                vb_trsm_tiles_kernel<<<dim3(T - k - 1, batch), TRSM_THREADS, trsm_smem, stream>>>(L, T, k, stride);
                 ++vb_launch_counter;
             }
             if (kk + 1 < pw) {
@@ -371,6 +382,8 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
                 p.j_hi = k0 + pw;
                 p.alpha = -1.0;
                 p.accumulate = 1;
+                p.batch = batch;
+                p.batch_stride = stride;
                 if ((err = vb_gemm_dispatch(p, stream)) != cudaSuccess) return err;
             }
         }
@@ -385,6 +398,8 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
             p.j_hi = T;
             p.alpha = -1.0;
             p.accumulate = 1;
+            p.batch = batch;
+            p.batch_stride = stride;
             if ((err = vb_gemm_dispatch(p, stream)) != cudaSuccess) return err;
         }
     }
@@ -394,7 +409,8 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
 // x (length T*128) is overwritten by the solution of L L^T x = b.
 int vb_solve_variant = 1;  // 1: one cooperative launch per sweep, 0: two launches per block row
 
-static cudaError_t solve_cooperative(const double *L, int T, double *x, int *flags, cudaStream_t stream)
+static cudaError_t solve_cooperative(const double *L, int T, double *x, int *flags, cudaStream_t stream, int batch,
+                                     long long stride)
 {
     const int smem = (VB_TILE * (VB_TILE + 1) + VB_TILE + 2 * SWEEP_THREADS) * (int)sizeof(double);
     cudaError_t err;
@@ -407,20 +423,33 @@ static cudaError_t solve_cooperative(const double *L, int T, double *x, int *fla
     if ((err = cudaFuncSetAttribute(vb_trisweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vb_trisweep_kernel<false>, SWEEP_THREADS, smem)) != cudaSuccess) return err;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const int grid = T < sms ? T : sms;
-    if ((err = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * T, stream)) != cudaSuccess) return err;
-    int *fl_f = flags, *fl_b = flags + T;
-    void *args_f[] = {(void *)&L, (void *)&T, (void *)&x, (void *)&fl_f};
-    void *args_b[] = {(void *)&L, (void *)&T, (void *)&x, (void *)&fl_b};
+    // every CTA of the launch must be co-resident (the flags spin): one CTA per SM, shared by the batch
+    int per_mat = sms * per_sm / batch;
+    if (per_mat < 1) return cudaErrorLaunchOutOfResources;
+    if (per_mat > T) per_mat = T;
+    const int grid = per_mat * batch;
+    if ((err = cudaMemsetAsync(flags, 0, sizeof(int) * 2 * T * batch, stream)) != cudaSuccess) return err;
+    int *fl_f = flags, *fl_b = flags + (long long)T * batch;
+    void *args_f[] = {(void *)&L, (void *)&T, (void *)&x, (void *)&fl_f, (void *)&batch, (void *)&stride};
+    void *args_b[] = {(void *)&L, (void *)&T, (void *)&x, (void *)&fl_b, (void *)&batch, (void *)&stride};
     if ((err = cudaLaunchCooperativeKernel((void *)vb_trisweep_kernel<false>, dim3(grid), dim3(SWEEP_THREADS), args_f, smem, stream)) != cudaSuccess) return err;
     if ((err = cudaLaunchCooperativeKernel((void *)vb_trisweep_kernel<true>, dim3(grid), dim3(SWEEP_THREADS), args_b, smem, stream)) != cudaSuccess) return err;
     vb_launch_counter += 2;
     return cudaGetLastError();
 }
 
-cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream)
+cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream, int batch,
+                           long long stride)
 {
-    if (vb_solve_variant == 1 && flags != nullptr) return solve_cooperative(L, T, x, flags, stream);
+    if (batch < 1) batch = 1;
+    if (vb_solve_variant == 1 && flags != nullptr) return solve_cooperative(L, T, x, flags, stream, batch, stride);
+    if (batch > 1) {
+        for (int b = 0; b < batch; ++b) {
+            cudaError_t eb = vb_solve_tiled(L + (long long)b * stride, T, x + (long long)b * T * VB_TILE, nullptr, stream, 1, 0);
+            if (eb != cudaSuccess) return eb;
+        }
+        return cudaSuccess;
+    }
     const int fwd_smem = VB_TILE_ELEMS * (int)sizeof(double);
     const int bwd_smem = VB_TILE * (VB_TILE + 1) * (int)sizeof(double);
     cudaError_t err;

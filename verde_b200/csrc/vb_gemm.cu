@@ -378,6 +378,7 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int STEPS_PER_CHUNK = VB_TILE / V2_KC;
     const int nsteps = p.nk * STEPS_PER_CHUNK;
+    const long long total = ntiles * (p.batch > 1 ? p.batch : 1);  // ntiles = tiles of ONE matrix
 
     if (tid == 0) {
         for (int s = 0; s < V2_STAGES; ++s) {
@@ -390,9 +391,11 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
 
     long long gstep = 0;  // ring position, continues across tiles
     if (warp == NCW) {
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             int bi, bj;
-            decode_tile(t, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+            const long long mat = t / ntiles;
+            decode_tile(t - mat * ntiles, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+            const long long moff = mat * p.batch_stride;
             const bool diag = (bi == bj) && (p.a_base == p.b_base);
             const unsigned stage_bytes = (diag ? 1u : 2u) * V2_KC * VB_TILE * (unsigned)sizeof(double);
             for (int step = 0; step < nsteps; ++step, ++gstep) {
@@ -406,8 +409,8 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
                 const int krow0 = (step % STEPS_PER_CHUNK) * V2_KC;
                 double *sA = smem + slot * V2_STAGE_DOUBLES;
                 double *sB = sA + V2_KC * LDS_STRIDE;
-                const double *gA = p.a_base + p.a_chunk_off[kk] + (long long)bj * VB_TILE_ELEMS + krow0 * VB_TILE;
-                const double *gB = p.b_base + p.b_chunk_off[kk] + (long long)bi * VB_TILE_ELEMS + krow0 * VB_TILE;
+                const double *gA = p.a_base + moff + p.a_chunk_off[kk] + (long long)bj * VB_TILE_ELEMS + krow0 * VB_TILE;
+                const double *gB = p.b_base + moff + p.b_chunk_off[kk] + (long long)bi * VB_TILE_ELEMS + krow0 * VB_TILE;
                 bulk_load(smem_u32(sA + lane * LDS_STRIDE), gA + lane * VB_TILE, VB_TILE * sizeof(double), full);
                 if (!diag)
                     bulk_load(smem_u32(sB + lane * LDS_STRIDE), gB + lane * VB_TILE, VB_TILE * sizeof(double), full);
@@ -418,9 +421,10 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
         const int q0 = (warp & 3) * 32;
         const int lk = lane & 3, lr = lane >> 2;
         const double alpha = p.alpha;
-        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
             int bi, bj;
-            decode_tile(t, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+            const long long mat = t / ntiles;
+            decode_tile(t - mat * ntiles, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
             const bool diag = (bi == bj) && (p.a_base == p.b_base);
             double acc[MI][4][2];
 #pragma unroll
@@ -450,7 +454,7 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars[V2_STAGES + slot]));
             }
-            double *ctile = p.c_base + vb_tile_index(bi, bj, p.T) * VB_TILE_ELEMS;
+            double *ctile = p.c_base + mat * p.batch_stride + vb_tile_index(bi, bj, p.T) * VB_TILE_ELEMS;
 #pragma unroll
             for (int a = 0; a < MI; ++a)
 #pragma unroll
@@ -616,6 +620,18 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
     const long long tiles = vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
     if (tiles <= 0) return cudaSuccess;
     cudaError_t e;
+    if (p.batch > 1 && vb_gemm_variant != 3) {
+        // only the persistent kernel walks a batch in one launch; the older variants go matrix by matrix
+        for (int b = 0; b < p.batch; ++b) {
+            VbGemmParams q = p_in;
+            q.batch = 1;
+            q.a_base += (long long)b * p.batch_stride;
+            q.b_base += (long long)b * p.batch_stride;
+            q.c_base += (long long)b * p.batch_stride;
+            if ((e = vb_launch_gemm(q, stream)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     if (vb_gemm_variant == 1) {
         e = cudaFuncSetAttribute(vb_gemm_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -629,7 +645,8 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
         }
         e = cudaFuncSetAttribute(vb_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+        const long long all_tiles = tiles * (p.batch > 1 ? p.batch : 1);
+        const unsigned grid = (unsigned)(all_tiles < sms ? all_tiles : sms);
         vb_gemm_persistent_kernel<<<grid, 8 * 32 + 32, V2_SMEM_BYTES, stream>>>(p, tiles);
     } else if (vb_gemm_variant == 2) {
         e = cudaFuncSetAttribute(vb_gemm_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);

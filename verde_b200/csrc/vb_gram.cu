@@ -134,6 +134,35 @@ vb_scale_system_kernel(double *__restrict__ G, int T, long long cols,
     }
 }
 
+// Same algebra for a damping sweep: G is read ONCE and one scaled, damped copy is written per
+// damping (L + b * stride); G itself is left untouched (SplineCV re-uses it).
+__global__ void __launch_bounds__(256)
+vb_scale_system_batched_kernel(const double *__restrict__ G, int T, long long cols,
+                               const double *__restrict__ inv_scale, const double *__restrict__ dampings,
+                               int batch, double *__restrict__ L, long long stride)
+{
+    long long t = blockIdx.x;
+    int bj = 0;
+    while (t >= T - bj) {
+        t -= T - bj;
+        ++bj;
+    }
+    const int bi = bj + (int)t;
+    const long long toff = (long long)blockIdx.x * VB_TILE_ELEMS;
+    const int r = threadIdx.x & (VB_TILE - 1);
+    const long long gr = (long long)bi * VB_TILE + r;
+    const double sr = inv_scale[gr];
+    for (int cc = threadIdx.x >> 7; cc < VB_TILE; cc += 2) {
+        const long long gc = (long long)bj * VB_TILE + cc;
+        const double v = G[toff + cc * VB_TILE + r] * sr * inv_scale[gc];
+        for (int b = 0; b < batch; ++b) {
+            double vb = v;
+            if (gr == gc) vb = (gr < cols) ? v + dampings[b] : 1.0;
+            L[(long long)b * stride + toff + cc * VB_TILE + r] = vb;
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t vb_launch_gram_panel(const VbGramProblem &prob, long long row0, int nchunk, int T,
@@ -173,6 +202,16 @@ cudaError_t vb_launch_scale_system(double *G, int T, long long cols, const doubl
                                    double damping, cudaStream_t stream)
 {
     vb_scale_system_kernel<<<(unsigned)vb_num_tiles(T), 256, 0, stream>>>(G, T, cols, inv_scale, damping);
+    ++vb_launch_counter;
+    return cudaGetLastError();
+}
+
+cudaError_t vb_launch_scale_system_batched(const double *G, int T, long long cols, const double *inv_scale,
+                                           const double *dampings_dev, int batch, double *L,
+                                           long long stride, cudaStream_t stream)
+{
+    vb_scale_system_batched_kernel<<<(unsigned)vb_num_tiles(T), 256, 0, stream>>>(G, T, cols, inv_scale,
+                                                                                  dampings_dev, batch, L, stride);
     ++vb_launch_counter;
     return cudaGetLastError();
 }

@@ -23,6 +23,10 @@ struct VbGemmParams {
     double alpha;
     int accumulate;  // 0: C = alpha*acc, 1: C += alpha*acc
     int strip;       // rasterisation strip width in block columns (filled by vb_launch_gemm)
+    // batch > 1: the same update on `batch` independent matrices (SplineCV's damping sweep); matrix b
+    // has every base pointer advanced by b * batch_stride doubles.  0 or 1 = a single matrix.
+    int batch;
+    long long batch_stride;
 };
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
@@ -102,7 +106,15 @@ struct VbFusedGramParams {
 cudaError_t vb_launch_fused_gram(const VbFusedGramParams &p, cudaStream_t stream);
 
 // Cholesky and solves on tile-packed storage (vb_chol.cu)
-cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream);
-// flags: 2*T ints of device scratch for the single-launch sweeps (null -> per-block-row kernels)
-cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream);
+// batch matrices of stride `stride` doubles are factored side by side (d_info: one int per matrix)
+cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream,
+                              int batch = 1, long long stride = 0);
+// flags: 2*T*batch ints of device scratch for the single-launch sweeps (null -> per-block-row kernels);
+// x holds batch right-hand sides of T*128 doubles each
+cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream,
+                           int batch = 1, long long stride = 0);
+// L_b = D G D + damping_b I for b < batch (reads G once)
+cudaError_t vb_launch_scale_system_batched(const double *G, int T, long long cols, const double *inv_scale,
+                                           const double *dampings_dev, int batch, double *L,
+                                           long long stride, cudaStream_t stream);
 extern int vb_solve_variant;

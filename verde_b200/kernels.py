@@ -226,6 +226,24 @@ class GramSystem:
         _cabi.check(rc, "gram_solve")
         return params
 
+    def solve_multi(self, total_rows, dampings):
+        """
+        Parameters for every damping of a sweep, shape (len(dampings), cols).  The Gram matrix is
+        kept; all damped systems are factored and solved side by side on the device
+        (``vb200_gram_solve_multi``).  A non-positive-definite system raises LinAlgError.
+        """
+        damp = np.ascontiguousarray([float(d) for d in dampings], dtype=np.float64)
+        for d in damp:
+            _require_damping(d)
+        params = np.empty((damp.size, self.cols), dtype=np.float64)
+        pivots = np.zeros(damp.size, dtype=np.int32)
+        self._torch.cuda.synchronize()
+        rc = self._lib.vb200_gram_solve_multi(_cabi.ptr(self.gram), _cabi.ptr(self.stats), self.cols,
+                                              int(total_rows), _cabi.ptr(damp), int(damp.size),
+                                              _cabi.ptr(params), _cabi.ptr(pivots), ctypes.byref(self.info))
+        _remember(self.info)
+        _cabi.check(rc, "gram_solve_multi")
+        return params
 
     def factor(self, total_rows, damping):
         "Scale, damp and factor in place (the Gram matrix becomes L); keeps 1/s for later solves."

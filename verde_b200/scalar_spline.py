@@ -20,6 +20,7 @@ least squares there, whose result depends on the scikit-learn version; it is
 outside this path and raises ``NotImplementedError`` at ``fit``.
 """
 import itertools
+import time
 import warnings
 
 import numpy as np
@@ -291,6 +292,8 @@ class SplineCV(BaseGridder):
         mindists, dampings = list(self.mindists), list(self.dampings)
         table = np.zeros((len(mindists), len(dampings), len(folds)))
         jobs = [(f, i) for f in range(len(folds)) for i in range(len(mindists))]
+        sweep = {"jobs": 0, "gram_ms": 0.0, "factor_ms": 0.0, "solve_ms": 0.0, "gemm_ms": 0.0, "gemm_flops": 0.0,
+                 "score_s": 0.0}
         for job in dist.round_robin(len(jobs)):
             fold, imd = jobs[job]
             train_index, test_index = folds[fold]
@@ -306,11 +309,18 @@ class SplineCV(BaseGridder):
             system = kernels.GramSystem(force_coords[0].size)
             system.accumulate(0, east, north, train[1][0], train_w, force_coords[0], force_coords[1],
                               mindists[imd])
-            for idamp, damping in enumerate(dampings):
-                force = system.solve(east.size, damping, keep=idamp + 1 < len(dampings))
-                frozen = _FrozenSpline(force, force_coords, mindists[imd])
+            # all dampings of this (fold, mindist) are factored and solved side by side on the device
+            forces = system.solve_multi(east.size, dampings)
+            for key in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms", "gemm_flops"):
+                sweep[key] += getattr(system.info, key)
+            t0 = time.perf_counter()
+            for idamp in range(len(dampings)):
+                frozen = _FrozenSpline(forces[idamp], force_coords, mindists[imd])
                 table[imd, idamp, fold] = score_estimator(scoring, frozen, *test)
+            sweep["score_s"] += time.perf_counter() - t0
+            sweep["jobs"] += 1
             del system
+        self.sweep_info_ = sweep
         table = dist.allreduce_sum_numpy(table)
         scores = table.mean(axis=2).reshape(-1)
         best = int(np.argmax(scores))
