@@ -236,6 +236,8 @@ def main():
     ap.add_argument("--size", type=int, default=50_000, help="data points per rank (default: the BASELINE 50k)")
     ap.add_argument("--grid", type=int, default=2000, help="grid is GRID x GRID per rank")
     ap.add_argument("--cpu-sample", type=int, default=14000, help="n=m of the CPU baseline sample")
+    ap.add_argument("--cholesky", default="auto", choices=["auto", "replicated", "distributed"],
+                    help="N > 1: replicated m x m Cholesky on every rank, or panel-cyclic over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -289,6 +291,8 @@ def main():
     d_force = torch.empty(m, dtype=torch.float64, device=dev)
     d_out = torch.empty(pb - pa, dtype=torch.float64, device=dev)
     system = kernels.GramSystem(m) if world > 1 else None
+    vb.dist.set_cholesky(args.cholesky)
+    dist_chol = world > 1 and vb.dist.use_distributed_cholesky((m + 127) // 128, 8, world)
     info = _cabi.FitInfo()
     phase = {}
 
@@ -313,9 +317,13 @@ def main():
                                            _cabi.ptr(system.gram), _cabi.ptr(system.stats), 0, ctypes.byref(info))
             _cabi.check(rc, "bench gram")
             system.allreduce()
-            rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, DAMPING, 0,
-                                      _cabi.ptr(d_force), ctypes.byref(info))
-            _cabi.check(rc, "bench solve")
+            if dist_chol:
+                system.info = info
+                system.solve_distributed(n_total, DAMPING, panel_tiles=8, out=d_force)
+            else:
+                rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, DAMPING, 0,
+                                          _cabi.ptr(d_force), ctypes.byref(info))
+                _cabi.check(rc, "bench solve")
         ev[1].record()
         rc = lib.vb200_predict(_cabi.ptr(d_gx), _cabi.ptr(d_gy), pb - pa, _cabi.ptr(d_fe), _cabi.ptr(d_fn),
                                _cabi.ptr(d_force), m, MINDIST, _cabi.ptr(d_out))
@@ -407,11 +415,15 @@ def main():
     fit_s = statistics.mean(fit_ms) * 1e-3
     pred_s = statistics.mean(pred_ms) * 1e-3
     n_pairs = (pb - pa) * m
-    algorithmic_fit_flops = (b - a) * m * (m + 1) + m**3 / 3.0
+    algorithmic_fit_flops = (b - a) * m * (m + 1) + m**3 / 3.0 / (world if dist_chol else 1)  # this rank's share
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(world, n_rank, m, args.grid),
+        "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(world, n_rank, m, args.grid),
+                       cholesky=("single GPU" if world == 1 else
+                                 "panel-cyclic over {} ranks, NCCL panel broadcast".format(world) if dist_chol else
+                                 "replicated on every rank")),
         "fit_s": fit_s, "predict_s": pred_s, "predict_gpts_per_s": (pb - pa) * world / pred_s * 1e-9,
         "predict_gpairs_per_s": n_pairs / pred_s * 1e-9,
         "fit_phases_ms": {k: phase["info"][k] for k in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms")},

@@ -143,6 +143,26 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
                            int64_t total_rows, const double *dampings, int32_t n_dampings,
                            double *out_params, int32_t *out_info, vb200_fit_info *info);
 
+/* ---- stepwise Cholesky for the multi-GPU panel-cyclic factorisation ---------------------------
+ * The replicated m x m Cholesky is the Amdahl term of the row-sharded fit.  These entry points expose
+ * its outer steps so that N ranks, each holding the all-reduced G, share the m^3/3 flops: outer
+ * panel p (pw block columns of 128) is owned by rank p % N, which factors it (chol_panel) and
+ * broadcasts the panel -- ONE contiguous range of the tile-packed triangle, chol_panel_range -- to
+ * the others (NCCL over NVLink, done by the caller); every rank then applies the panel to the
+ * block columns IT owns (chol_update).  After the last panel every rank holds the complete factor
+ * and chol_finish runs the substitution.  begin/panel/update only enqueue work on the library
+ * stream (no host synchronisation); finish synchronises and reports like vb200_gram_solve.
+ * One factorisation at a time per process.  verde_b200/kernels.py::GramSystem.solve_distributed
+ * is the driver. */
+int vb200_chol_begin(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
+                     double damping);
+int vb200_chol_panel_range(int64_t cols, int32_t k0, int32_t pw, int64_t *offset, int64_t *count);
+int vb200_chol_panel(double *chol_dev, int64_t cols, int32_t k0, int32_t pw);
+int vb200_chol_update(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, int32_t j_lo,
+                      int32_t j_hi);
+int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params,
+                      vb200_fit_info *info);
+
 /* ---- factor once, solve many right-hand sides (Vector of Splines on shared coordinates) ------
  * factor:  like vb200_gram_solve but stops after the Cholesky factorisation: gram_dev is overwritten
  *          by L (tile-packed) and inv_scale_dev (DEVICE, vb200_padded_cols(cols) doubles) receives

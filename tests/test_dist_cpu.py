@@ -60,7 +60,36 @@ def _worker(rank, world, port, out_dir):
         table[j] = 10.0 + j
     table = dist.allreduce_sum_numpy(table)
     np.testing.assert_array_equal(table, 10.0 + np.arange(7))
-    # 4. turning sharding off makes the helpers local again
+    # 4. panel-cyclic Cholesky: the schedule + broadcast the GPU driver (GramSystem.solve_distributed)
+    #    uses, with numpy standing in for the panel / update kernels on a dense SPD matrix
+    import torch
+
+    nb, blk, pw = 11, 8, 3  # 11 block columns of 8, outer panels of 3 block columns
+    m = nb * blk
+    x = np.random.RandomState(9).normal(size=(3 * m, m))
+    a_full = x.T @ x + 1e-3 * np.eye(m)
+    work = torch.from_numpy(a_full.copy())  # every rank starts from the all-reduced matrix
+    mat = work.numpy()
+    schedule = dist.panel_cyclic_schedule(nb, pw, world)
+    assert [o for _, _, o in schedule] == [0, 1, 0, 1] and schedule[-1][:2] == (9, 2)
+    for p, (k0, width, owner) in enumerate(schedule):
+        c0, c1 = k0 * blk, (k0 + width) * blk
+        if rank == owner:  # "chol_panel": factor the diagonal block, solve the rows below
+            mat[c0:c1, c0:c1] = np.linalg.cholesky(mat[c0:c1, c0:c1])
+            mat[c1:, c0:c1] = np.linalg.solve(mat[c0:c1, c0:c1], mat[c1:, c0:c1].T).T
+        panel = work[:, c0:c1].contiguous()
+        dist.broadcast_(panel, owner)
+        work[:, c0:c1] = panel
+        for q0, qwidth, qowner in schedule[p + 1:]:
+            if qowner == rank:  # "chol_update" of the block columns this rank owns
+                j0, j1 = q0 * blk, (q0 + qwidth) * blk
+                mat[j0:, j0:j1] -= mat[j0:, c0:c1] @ mat[j0:j1, c0:c1].T
+    np.testing.assert_allclose(np.tril(mat), np.linalg.cholesky(a_full), rtol=0, atol=1e-10)
+    assert dist.use_distributed_cholesky(391, 8) and not dist.use_distributed_cholesky(24, 8)
+    dist.set_cholesky("replicated")
+    assert not dist.use_distributed_cholesky(391, 8)
+    dist.set_cholesky("auto")
+    # 5. turning sharding off makes the helpers local again
     dist.set_sharding(False)
     assert not dist.sharding_active()
     dist.set_sharding("auto")
@@ -87,3 +116,9 @@ def test_shard_bounds_cover_everything():
     assert dist.world() == (0, 1) and not dist.sharding_active()
     with pytest.raises(ValueError):
         dist.set_sharding("maybe")
+    with pytest.raises(ValueError):
+        dist.set_cholesky("sometimes")
+    sched = dist.panel_cyclic_schedule(391, 8, 8)
+    assert len(sched) == 49 and sched[0] == (0, 8, 0) and sched[-1] == (384, 7, 0) and sched[9] == (72, 8, 1)
+    assert sum(w for _, w, _ in sched) == 391
+    assert not dist.use_distributed_cholesky(391, 8, 1)

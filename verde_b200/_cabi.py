@@ -65,6 +65,11 @@ SIGNATURES = {
     "vb200_gram_accumulate": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl] + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.POINTER(FitInfo)]),
     "vb200_gram_solve": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_gram_solve_multi": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+    "vb200_chol_begin": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl]),
+    "vb200_chol_panel_range": (ctypes.c_int, [i64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+    "vb200_chol_panel": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_int32, ctypes.c_int32]),
+    "vb200_chol_update": (ctypes.c_int, [ctypes.c_void_p, i64] + [ctypes.c_int32] * 4),
+    "vb200_chol_finish": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_padded_cols": (i64, [i64]),
     "vb200_gram_factor": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_chol_solve": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [ctypes.POINTER(FitInfo)]),

@@ -770,6 +770,127 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
     return 0;
 }
 
+// ---- stepwise factorisation for the multi-GPU panel-cyclic Cholesky ------------------------------
+// State between begin / panel / update / finish lives in the cached workspace (inv_scale, rhs, info)
+// and in g_step; all launches are asynchronous on the library stream until finish.
+namespace {
+struct StepState {
+    bool open = false;
+    int T = 0;
+    long long cols = 0;
+    Span fac;
+    long long launches0 = 0;
+} g_step;
+}  // namespace
+
+int vb200_chol_begin(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows, double damping)
+{
+    if (cols <= 0 || total_rows <= 0) return fail(VB200_E_BADARG, "bad sizes");
+    if (!gram_dev || !stats_dev) return fail(VB200_E_BADARG, "null pointer");
+    if (!(damping > 0.0)) return fail(VB200_E_BADARG, "damping must be > 0 (the damping=None branch of the reference is out of scope)");
+    if (!is_device_ptr(gram_dev) || !is_device_ptr(stats_dev))
+        return fail(VB200_E_BADARG, "gram/stats buffers must be device memory");
+    cudaStream_t st = 0;
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    double *inv_scale, *rhs;
+    int *d_info;
+    CU(ws_get("inv_scale", sizeof(double) * Mpad, (void **)&inv_scale));
+    CU(ws_get("rhs", sizeof(double) * Mpad, (void **)&rhs));
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    prof_reset();
+    g_step.open = true;
+    g_step.T = T;
+    g_step.cols = cols;
+    g_step.launches0 = vb_launch_counter;
+    CU(span_begin(&g_step.fac, st));
+    CU(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+    CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale, rhs, st));
+    CU(vb_launch_scale_system(gram_dev, T, cols, inv_scale, damping, st));
+    return 0;
+}
+
+int vb200_chol_panel_range(int64_t cols, int32_t k0, int32_t pw, int64_t *offset, int64_t *count)
+{
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    if (cols <= 0 || k0 < 0 || pw < 1 || k0 + pw > T || !offset || !count) return fail(VB200_E_BADARG, "bad panel range");
+    *offset = vb_chol_column_offset(k0, T);
+    *count = vb_chol_column_offset(k0 + pw, T) - *offset;
+    return 0;
+}
+
+int vb200_chol_panel(double *chol_dev, int64_t cols, int32_t k0, int32_t pw)
+{
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    if (!g_step.open || g_step.cols != cols) return fail(VB200_E_BADARG, "vb200_chol_begin was not called for this system");
+    if (!chol_dev || k0 < 0 || pw < 1 || pw > VB_MAX_KCHUNKS || k0 + pw > T) return fail(VB200_E_BADARG, "bad panel");
+    int *d_info;
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    CU(vb_chol_factor_panel(chol_dev, T, k0, pw, d_info, 0));
+    return 0;
+}
+
+int vb200_chol_update(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, int32_t j_lo, int32_t j_hi)
+{
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    if (!g_step.open || g_step.cols != cols) return fail(VB200_E_BADARG, "vb200_chol_begin was not called for this system");
+    if (!chol_dev || k0 < 0 || pw < 1 || pw > VB_MAX_KCHUNKS || k0 + pw > T || j_lo < k0 + pw || j_hi > T)
+        return fail(VB200_E_BADARG, "bad update range");
+    CU(vb_chol_trailing_update(chol_dev, T, k0, pw, j_lo, j_hi, 0));
+    return 0;
+}
+
+int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, vb200_fit_info *info)
+{
+    if (!g_step.open || g_step.cols != cols) return fail(VB200_E_BADARG, "vb200_chol_begin was not called for this system");
+    if (!chol_dev || !out_params) return fail(VB200_E_BADARG, "null pointer");
+    g_step.open = false;
+    cudaStream_t st = 0;
+    const int T = g_step.T;
+    const long long Mpad = (long long)T * VB_TILE;
+    double *inv_scale, *rhs, *mm;
+    int *d_info, *d_flags;
+    CU(ws_get("inv_scale", sizeof(double) * Mpad, (void **)&inv_scale));
+    CU(ws_get("rhs", sizeof(double) * Mpad, (void **)&rhs));
+    CU(ws_get("minmax", sizeof(double) * 2, (void **)&mm));
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    CU(ws_get("sweep_flags", sizeof(int) * 2 * T, (void **)&d_flags));
+    OutBuf ob;
+    CU(stage_out("out_params", out_params, cols, &ob));
+    CU(cudaEventRecord(g_step.fac.b, st));
+    Span sol;
+    CU(span_begin(&sol, st));
+    CU(vb_solve_tiled(chol_dev, T, rhs, d_flags, st));
+    vb_unscale_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(rhs, inv_scale, cols, ob.dev);
+    vb_diag_minmax_kernel<<<1, 256, 0, st>>>(chol_dev, T, cols, mm);
+    vb_launch_counter += 2;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(sol.b, st));
+    CU(finish_out(ob, st));
+    int h_info = 0;
+    double h_mm[2] = {0, 0};
+    CU(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_mm, mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double fms = span_ms(g_step.fac), sms = span_ms(sol);
+    if (info) {
+        info->block_rows = T;
+        info->cols = cols;
+        info->factor_ms += fms;
+        info->solve_ms += sms;
+        info->info = h_info;
+        info->diag_min = h_mm[0];
+        info->diag_max = h_mm[1];
+        info->kernel_launches += vb_launch_counter - g_step.launches0;
+    }
+    prof_collect(info);
+    if (h_info > 0) {
+        fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
+        return h_info;
+    }
+    return 0;
+}
+
 int64_t vb200_padded_cols(int64_t cols) { return (cols + VB_TILE - 1) / VB_TILE * VB_TILE; }
 
 int vb200_gram_factor(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,

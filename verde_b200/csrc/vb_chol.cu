@@ -347,61 +347,89 @@ long long col_base(int c, int T)
 
 }  // namespace
 
-cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream, int batch,
-                              long long stride)
+static cudaError_t chol_set_attributes(int *potrf_smem, int *trsm_smem)
 {
-    if (batch < 1) batch = 1;
     cudaError_t err;
-    const int potrf_smem = VB_TILE_ELEMS * (int)sizeof(double);
-    const int trsm_smem = VB_TILE_ELEMS * (int)sizeof(double);
-    if ((err = cudaFuncSetAttribute(vb_potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(vb_trsm_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem)) != cudaSuccess) return err;
-    if (panel_tiles < 1) panel_tiles = 1;
-    if (panel_tiles > VB_MAX_KCHUNKS) panel_tiles = VB_MAX_KCHUNKS;
-    if ((err = cudaMemsetAsync(d_info, 0, sizeof(int) * batch, stream)) != cudaSuccess) return err;
+    *potrf_smem = VB_TILE_ELEMS * (int)sizeof(double);
+    *trsm_smem = VB_TILE_ELEMS * (int)sizeof(double);
+    if ((err = cudaFuncSetAttribute(vb_potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *potrf_smem)) != cudaSuccess) return err;
+    return cudaFuncSetAttribute(vb_trsm_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *trsm_smem);
+}
 
-    for (int k0 = 0; k0 < T; k0 += panel_tiles) {
-        const int pw = (T - k0 < panel_tiles) ? (T - k0) : panel_tiles;
-        for (int kk = 0; kk < pw; ++kk) {
-            const int k = k0 + kk;
-            vb_potrf_tile_kernel<<<batch, POTRF_THREADS, potrf_smem, stream>>>(
-                L + vb_tile_index(k, k, T) * VB_TILE_ELEMS, k, d_info, stride);
+// Factor the outer panel of block columns [k0, k0 + pw): potrf + trsm per column and the rank-128
+// updates of the panel's own remaining columns.  Everything left of k0 must already be applied.
+cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, cudaStream_t stream, int batch,
+                                 long long stride)
+{
+    cudaError_t err;
+    int potrf_smem, trsm_smem;
+    if ((err = chol_set_attributes(&potrf_smem, &trsm_smem)) != cudaSuccess) return err;
+    if (batch < 1) batch = 1;
+    for (int kk = 0; kk < pw; ++kk) {
+        const int k = k0 + kk;
+        vb_potrf_tile_kernel<<<batch, POTRF_THREADS, potrf_smem, stream>>>(
+            L + vb_tile_index(k, k, T) * VB_TILE_ELEMS, k, d_info, stride);
+        ++vb_launch_counter;
+        if (k + 1 < T) {
+            vb_trsm_tiles_kernel<<<dim3(T - k - 1, batch), TRSM_THREADS, trsm_smem, stream>>>(L, T, k, stride);
             ++vb_launch_counter;
-            if (k + 1 < T) {
-                vb_trsm_tiles_kernel<<<dim3(T - k - 1, batch), TRSM_THREADS, trsm_smem, stream>>>(L, T, k, stride);
-                ++vb_launch_counter;
-            }
-            if (kk + 1 < pw) {
-                VbGemmParams p = {};
-                p.a_base = p.b_base = L;
-                p.a_chunk_off[0] = p.b_chunk_off[0] = col_base(k, T);
-                p.nk = 1;
-                p.c_base = L;
-                p.T = T;
-                p.j_lo = k + 1;
-                p.j_hi = k0 + pw;
-                p.alpha = -1.0;
-                p.accumulate = 1;
-                p.batch = batch;
-                p.batch_stride = stride;
-                if ((err = vb_gemm_dispatch(p, stream)) != cudaSuccess) return err;
-            }
         }
-        if (k0 + pw < T) {
+        if (kk + 1 < pw) {
             VbGemmParams p = {};
             p.a_base = p.b_base = L;
-            for (int kk = 0; kk < pw; ++kk) p.a_chunk_off[kk] = p.b_chunk_off[kk] = col_base(k0 + kk, T);
-            p.nk = pw;
+            p.a_chunk_off[0] = p.b_chunk_off[0] = col_base(k, T);
+            p.nk = 1;
             p.c_base = L;
             p.T = T;
-            p.j_lo = k0 + pw;
-            p.j_hi = T;
+            p.j_lo = k + 1;
+            p.j_hi = k0 + pw;
             p.alpha = -1.0;
             p.accumulate = 1;
             p.batch = batch;
             p.batch_stride = stride;
             if ((err = vb_gemm_dispatch(p, stream)) != cudaSuccess) return err;
         }
+    }
+    return cudaGetLastError();
+}
+
+// Trailing update C(:, [j_lo, j_hi)) -= L(:, panel) L([j_lo, j_hi), panel)^T with the factored panel
+// [k0, k0 + pw): the bulk of the m^3/3 flops, one launch of the DMMA tile kernel (K = 128 * pw).
+cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, int j_hi, cudaStream_t stream,
+                                    int batch, long long stride)
+{
+    if (j_lo < k0 + pw) j_lo = k0 + pw;
+    if (j_hi > T) j_hi = T;
+    if (j_lo >= j_hi) return cudaSuccess;
+    VbGemmParams p = {};
+    p.a_base = p.b_base = L;
+    for (int kk = 0; kk < pw; ++kk) p.a_chunk_off[kk] = p.b_chunk_off[kk] = col_base(k0 + kk, T);
+    p.nk = pw;
+    p.c_base = L;
+    p.T = T;
+    p.j_lo = j_lo;
+    p.j_hi = j_hi;
+    p.alpha = -1.0;
+    p.accumulate = 1;
+    p.batch = batch < 1 ? 1 : batch;
+    p.batch_stride = stride;
+    return vb_gemm_dispatch(p, stream);
+}
+
+long long vb_chol_column_offset(int c, int T) { return col_base(c, T) + (long long)c * VB_TILE_ELEMS; }
+
+cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream, int batch,
+                              long long stride)
+{
+    cudaError_t err;
+    if (batch < 1) batch = 1;
+    if (panel_tiles < 1) panel_tiles = 1;
+    if (panel_tiles > VB_MAX_KCHUNKS) panel_tiles = VB_MAX_KCHUNKS;
+    if ((err = cudaMemsetAsync(d_info, 0, sizeof(int) * batch, stream)) != cudaSuccess) return err;
+    for (int k0 = 0; k0 < T; k0 += panel_tiles) {
+        const int pw = (T - k0 < panel_tiles) ? (T - k0) : panel_tiles;
+        if ((err = vb_chol_factor_panel(L, T, k0, pw, d_info, stream, batch, stride)) != cudaSuccess) return err;
+        if ((err = vb_chol_trailing_update(L, T, k0, pw, k0 + pw, T, stream, batch, stride)) != cudaSuccess) return err;
     }
     return cudaGetLastError();
 }

@@ -109,6 +109,15 @@ cudaError_t vb_launch_fused_gram(const VbFusedGramParams &p, cudaStream_t stream
 // batch matrices of stride `stride` doubles are factored side by side (d_info: one int per matrix)
 cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream,
                               int batch = 1, long long stride = 0);
+// the two halves of one outer step of vb_cholesky_tiled, exposed for the multi-GPU panel-cyclic
+// factorisation (the owner of a panel factors it, everybody updates the columns it owns)
+cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, cudaStream_t stream,
+                                 int batch = 1, long long stride = 0);
+cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, int j_hi,
+                                    cudaStream_t stream, int batch = 1, long long stride = 0);
+// offset (doubles) of the diagonal tile of block column c: columns [c0, c1) occupy the contiguous
+// range [vb_chol_column_offset(c0), vb_chol_column_offset(c1)) of the tile-packed triangle
+long long vb_chol_column_offset(int c, int T);
 // flags: 2*T*batch ints of device scratch for the single-launch sweeps (null -> per-block-row kernels);
 // x holds batch right-hand sides of T*128 doubles each
 cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaStream_t stream,

@@ -8,8 +8,11 @@ What shards and how:
                accumulates the partial normal equations of ITS rows (G, J^T W d and
                the column statistics are all plain sums over rows); ONE all-reduce
                (sum, float64) of the packed lower triangle + the 4*M statistics
-               vector follows; the m x m Cholesky then runs replicated on every rank
-               (it is the serial part: Amdahl).
+               vector follows.  The m x m Cholesky is then shared too: outer panels
+               (8 block columns) are owned cyclically, the owner factors its panel and
+               broadcasts it (one contiguous range of the tile-packed triangle), every
+               rank applies it to the block columns it owns; the substitution runs
+               replicated on the complete factor (``set_cholesky``).
 * predict   -- the raveled prediction points are split into contiguous ranges; no
                communication during compute, one all-gather of the results.
 * SplineCV  -- independent (fold, mindist) Gram jobs are dealt round-robin to ranks;
@@ -65,6 +68,54 @@ def round_robin(njobs, rank=None, size=None):
     if rank is None or size is None:
         rank, size = world()
     return list(range(rank, int(njobs), size))
+
+
+_CHOLESKY = "auto"
+
+
+def set_cholesky(mode):
+    """
+    How the m x m Cholesky of a row-sharded fit runs on N > 1 ranks: ``"replicated"`` (every rank
+    factors the all-reduced matrix: the Amdahl term), ``"distributed"`` (outer panels owned
+    cyclically, panel broadcast over NCCL, each rank updates its own block columns) or ``"auto"``
+    (distributed when there are at least two outer panels per rank).
+    """
+    global _CHOLESKY
+    if mode not in ("auto", "replicated", "distributed"):
+        raise ValueError("cholesky mode must be 'auto', 'replicated' or 'distributed'")
+    _CHOLESKY = mode
+
+
+def panel_cyclic_schedule(block_rows, panel_tiles, size):
+    """
+    Outer panels of the tiled Cholesky and their owners: a list of ``(k0, width, owner)`` covering
+    block columns ``0..block_rows`` in panels of *panel_tiles*, panel p owned by rank ``p % size``.
+    """
+    block_rows, panel_tiles, size = int(block_rows), int(panel_tiles), int(size)
+    if block_rows < 1 or panel_tiles < 1 or size < 1:
+        raise ValueError("block_rows, panel_tiles and size must be positive")
+    return [(k0, min(panel_tiles, block_rows - k0), p % size)
+            for p, k0 in enumerate(range(0, block_rows, panel_tiles))]
+
+
+def use_distributed_cholesky(block_rows, panel_tiles, size=None):
+    "Decision rule of ``set_cholesky``; identical on every rank (it only depends on sizes)."
+    if size is None:
+        size = world()[1]
+    if size < 2 or _CHOLESKY == "replicated":
+        return False
+    if _CHOLESKY == "distributed":
+        return True
+    return len(panel_cyclic_schedule(block_rows, panel_tiles, size)) >= 2 * size
+
+
+def broadcast_(tensor, src):
+    "In-place broadcast of a torch tensor from rank *src* (NCCL for CUDA tensors, gloo for CPU)."
+    import torch.distributed as td
+
+    if world()[1] > 1:
+        td.broadcast(tensor, src=src)
+    return tensor
 
 
 def allreduce_sum_(tensor):

@@ -245,6 +245,41 @@ class GramSystem:
         _cabi.check(rc, "gram_solve_multi")
         return params
 
+    def solve_distributed(self, total_rows, damping, panel_tiles=8, out=None):
+        """
+        Like ``solve`` on N > 1 ranks that all hold the all-reduced Gram matrix, but the m^3/3
+        flops of the Cholesky are shared: outer panel p is factored by rank ``p % N`` and broadcast
+        (NCCL), every rank applies it to the block columns it owns.  All ranks return the same
+        parameters.  Everything between ``vb200_chol_begin`` and ``vb200_chol_finish`` is enqueued
+        without host synchronisation; NCCL orders itself against the library stream (the legacy
+        default stream, torch's current stream).
+        """
+        from . import dist
+
+        _require_damping(damping)
+        rank, size = dist.world()
+        lib, cols = self._lib, self.cols
+        block_rows = (cols + 127) // 128
+        schedule = dist.panel_cyclic_schedule(block_rows, panel_tiles, size)
+        gram_ptr = _cabi.ptr(self.gram)
+        _cabi.check(lib.vb200_chol_begin(gram_ptr, _cabi.ptr(self.stats), cols, int(total_rows), float(damping)),
+                    "chol_begin")
+        offset, count = ctypes.c_int64(), ctypes.c_int64()
+        for p, (k0, width, owner) in enumerate(schedule):
+            if rank == owner:
+                _cabi.check(lib.vb200_chol_panel(gram_ptr, cols, k0, width), "chol_panel")
+            _cabi.check(lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count)),
+                        "chol_panel_range")
+            dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
+            for q0, qwidth, qowner in schedule[p + 1:]:
+                if qowner == rank:
+                    _cabi.check(lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth), "chol_update")
+        params = np.empty(cols, dtype=np.float64) if out is None else out  # host array or CUDA tensor
+        rc = lib.vb200_chol_finish(gram_ptr, cols, _cabi.ptr(params), ctypes.byref(self.info))
+        _remember(self.info)
+        _cabi.check(rc, "chol_finish")
+        return params
+
     def factor(self, total_rows, damping):
         "Scale, damp and factor in place (the Gram matrix becomes L); keeps 1/s for later solves."
         _require_damping(damping)
@@ -310,6 +345,8 @@ def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindi
     system = GramSystem(cols)
     system.accumulate(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson)
     system.allreduce()
+    if dist.use_distributed_cholesky((cols + 127) // 128, 8):
+        return system.solve_distributed(rows, damping, panel_tiles=8)
     return system.solve(rows, damping)
 
 
