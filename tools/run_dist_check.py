@@ -30,6 +30,12 @@ single = vb.Spline(damping=1e-4).fit((e, n), d, weights=w)
 vb.dist.set_sharding("auto")
 out["spline_sharded_vs_single"] = float(np.max(np.abs(sp.force_ - single.force_)) / np.max(np.abs(single.force_)))
 
+# the same fit with the panel-cyclic Cholesky forced on (tiny system: 2 outer panels of 1 block column)
+vb.dist.set_cholesky("distributed")
+spd = vb.Spline(damping=1e-4).fit((e, n), d, weights=w)
+vb.dist.set_cholesky("auto")
+out["spline_distributed_cholesky_vs_replicated"] = float(np.max(np.abs(spd.force_ - sp.force_)) / np.max(np.abs(sp.force_)))
+
 v = np.load(os.path.join(ROOT, "tests/golden/vector_small.npz"))
 vs = vb.VectorSpline2D(damping=1e-3).fit((v["east"], v["north"]), (v["data_east"], v["data_north"]))
 out["vector_force_vs_ref"] = float(np.max(np.abs(vs.force_ - v["force_d1em3"])) / np.max(np.abs(v["force_d1em3"])))
@@ -41,7 +47,7 @@ cv = vb.SplineCV(dampings=list(c["dampings"]), mindists=list(c["mindists"])).fit
 out["cv_scores_vs_ref"] = float(np.max(np.abs(cv.scores_ - c["scores"])))
 out["cv_best"] = [float(cv.mindist_), float(cv.damping_), float(c["best_mindist"]), float(c["best_damping"])]
 out["cv_grid_vs_ref"] = float(np.max(np.abs(cv.predict((c["grid_east"], c["grid_north"])) - c["grid"])) / np.ptp(c["data"]))
-ok = (out["spline_force_vs_ref"] < 1e-5 and out["spline_grid_vs_ref"] < 1e-6 and out["vector_force_vs_ref"] < 1e-6
+ok = (out["spline_distributed_cholesky_vs_replicated"] < 1e-9 and out["spline_force_vs_ref"] < 1e-5 and out["spline_grid_vs_ref"] < 1e-6 and out["vector_force_vs_ref"] < 1e-6
       and out["cv_scores_vs_ref"] < 1e-7 and out["cv_best"][:2] == out["cv_best"][2:] and out["cv_grid_vs_ref"] < 1e-6)
 out["ok"] = bool(ok)
 if rank == 0:
