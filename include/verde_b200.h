@@ -181,6 +181,40 @@ int vb200_jacobian_transpose_apply(const double *east, const double *north, int6
                                    const double *force_east, const double *force_north, int64_t m,
                                    double mindist, const double *v, double *out);
 
+/* ---- either side of the spline path ---------------------------------
+ * block_split: replaces verde/coordinates.py:848-946 block_split(coordinates, ...): every point gets the
+ *         index of the nearest block centre, label = i_north * n_east + i_east over the centre grid the
+ *         host builds exactly like the reference (grid_coordinates(..., pixel_register=True)).  The
+ *         reference asks a KD-tree; centres are a product grid, so the nearest centre is the nearest
+ *         per axis.  Exact ties go to the lower index (the KD-tree's choice depends on its traversal).
+ *         labels (n int64, host or device) may be NULL.  n_blocks receives the number of NON-EMPTY
+ *         blocks.  The sorted (block, point) order stays cached for the calls below.
+ * block_ids: ascending labels of the non-empty blocks (n_blocks int64).
+ * block_aggregate: replaces the pandas groupby().aggregate(...) of verde/blockreduce.py:175-186 and
+ *         406-506 for one column: out[k] = reduction over the points of the k-th non-empty block,
+ *         visited in original point order.  weights is only read by the weighted reductions. */
+#define VB200_REDUCE_MEAN 0
+#define VB200_REDUCE_SUM 1
+#define VB200_REDUCE_MIN 2
+#define VB200_REDUCE_MAX 3
+#define VB200_REDUCE_COUNT 4
+#define VB200_REDUCE_MEDIAN 5
+#define VB200_REDUCE_VAR 6       /* sample variance, ddof = 1 (pandas "var") */
+#define VB200_REDUCE_WMEAN 7     /* numpy.average(values, weights=w) */
+#define VB200_REDUCE_WVAR 8      /* numpy.average((values - wmean)**2, weights=w) */
+#define VB200_REDUCE_INV_SUM_W 9 /* 1 / sum(w) */
+int vb200_block_split(const double *east, const double *north, int64_t n, const double *centers_east,
+                      int32_t n_east, const double *centers_north, int32_t n_north, int64_t *labels,
+                      int64_t *n_blocks);
+int vb200_block_ids(int64_t *ids);
+int vb200_block_aggregate(const double *values, const double *weights, int64_t n, int32_t op,
+                          double *out);
+/* distance_mask: replaces verde/mask.py:104-109 (KD-tree nearest-neighbour distance <= maxdist):
+ *         mask[i] = 1 when some data point lies within maxdist of (east[i], north[i]), else 0.
+ *         mask: n_points bytes, host or device. */
+int vb200_distance_mask(const double *data_east, const double *data_north, int64_t n, double maxdist,
+                        const double *east, const double *north, int64_t n_points, uint8_t *mask);
+
 /* ---- least squares on an explicit Jacobian ----------------------------------------------
  * replaces verde/base/least_squares.py:17 least_squares(jacobian, data, weights, damping):
  * jac row-major (n, m); damped branch only (damping > 0). */

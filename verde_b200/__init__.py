@@ -9,6 +9,7 @@ sm_100a CUDA kernels behind the C ABI of ``include/verde_b200.h``
 from . import dist  # noqa: F401
 from ._cabi import EngineError  # noqa: F401
 from .base import BaseGridder, GridResult, check_fit_input, n_1d_arrays, score_estimator  # noqa: F401
+from .blockreduce import BlockMean, BlockReduce, block_split, variance_to_weights  # noqa: F401
 from .checkerboard import CheckerBoard  # noqa: F401
 from .compose import Chain, Vector  # noqa: F401
 from .coords import (  # noqa: F401
@@ -20,6 +21,7 @@ from .coords import (  # noqa: F401
 )
 from .elastic_spline import VectorSpline2D  # noqa: F401
 from .kernels import least_squares  # noqa: F401
+from .mask import distance_mask  # noqa: F401
 from .scalar_spline import Spline, SplineCV, cross_val_score, fit_score, select  # noqa: F401
 
 __version__ = "0.1.0"

@@ -162,6 +162,15 @@ class GridResult:
     def __iter__(self):
         return iter(self.data_vars)
 
+    def where(self, mask):
+        "Like ``xarray.Dataset.where``: a copy with every data variable set to NaN where *mask* is False."
+        mask = np.asarray(mask, dtype=bool)
+        data_vars = {name: (dims, np.where(mask, np.asarray(values, dtype=np.float64), np.nan))
+                     for name, (dims, values) in self.data_vars.items()}
+        out = GridResult(data_vars, self.coords, self.dims)
+        out.attrs = dict(self.attrs)
+        return out
+
     def __repr__(self):
         shape = next(iter(self.data_vars.values()))[1].shape if self.data_vars else ()
         return "<GridResult dims={} shape={} data_vars={}>".format(self.dims, shape, list(self.data_vars))

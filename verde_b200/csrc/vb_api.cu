@@ -891,6 +891,188 @@ int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, 
     return 0;
 }
 
+// ---- block reductions and the distance mask (kernels in vb_block.cu) -------
+namespace {
+struct BlockState {
+    bool open = false;
+    long long n = 0, nseg = 0;
+    VbBlockWorkspace ws = {};
+    long long *labels = nullptr;
+} g_block;
+
+__global__ void vb_bbox_partial_kernel(const double *__restrict__ e, const double *__restrict__ n_, long long n,
+                                       double *__restrict__ out4)
+{
+    __shared__ double s[4][256];
+    double xmin = 1.0 / 0.0, xmax = -1.0 / 0.0, ymin = 1.0 / 0.0, ymax = -1.0 / 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        xmin = fmin(xmin, e[i]);
+        xmax = fmax(xmax, e[i]);
+        ymin = fmin(ymin, n_[i]);
+        ymax = fmax(ymax, n_[i]);
+    }
+    s[0][threadIdx.x] = xmin;
+    s[1][threadIdx.x] = xmax;
+    s[2][threadIdx.x] = ymin;
+    s[3][threadIdx.x] = ymax;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) {
+            s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + st]);
+            s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + st]);
+            s[2][threadIdx.x] = fmin(s[2][threadIdx.x], s[2][threadIdx.x + st]);
+            s[3][threadIdx.x] = fmax(s[3][threadIdx.x], s[3][threadIdx.x + st]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out4[blockIdx.x * 4 + threadIdx.x] = s[threadIdx.x][0];
+}
+}  // namespace
+
+int vb200_block_split(const double *east, const double *north, int64_t n, const double *centers_east,
+                      int32_t n_east, const double *centers_north, int32_t n_north, int64_t *labels,
+                      int64_t *n_blocks)
+{
+    g_block.open = false;
+    if (n < 0 || n_east < 1 || n_north < 1) return fail(VB200_E_BADARG, "bad sizes");
+    if (n > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many points (limit 2^31 - 1)");
+    if (!n_blocks || !centers_east || !centers_north || (n > 0 && (!east || !north))) return fail(VB200_E_BADARG, "null pointer");
+    cudaStream_t st = 0;
+    if (n == 0) {
+        *n_blocks = 0;
+        g_block.open = true;
+        g_block.n = 0;
+        g_block.nseg = 0;
+        return 0;
+    }
+    const double *de, *dn, *dce, *dcn;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("blk_ce", centers_east, n_east, &dce, st));
+    CU(stage_in("blk_cn", centers_north, n_north, &dcn, st));
+    VbBlockWorkspace &ws = g_block.ws;
+    const long long ntiles = (n + 2047) / 2048;
+    const long long scan_elems = vb_block_scan_scratch_elems(256 * ntiles > n ? 256 * ntiles : n) + 16;
+    CU(ws_get("blk_keys0", sizeof(uint64_t) * n, (void **)&ws.keys[0]));
+    CU(ws_get("blk_keys1", sizeof(uint64_t) * n, (void **)&ws.keys[1]));
+    CU(ws_get("blk_vals0", sizeof(unsigned) * n, (void **)&ws.vals[0]));
+    CU(ws_get("blk_vals1", sizeof(unsigned) * n, (void **)&ws.vals[1]));
+    CU(ws_get("blk_counts", sizeof(unsigned) * 256 * ntiles, (void **)&ws.counts));
+    CU(ws_get("blk_scratch", sizeof(unsigned) * scan_elems, (void **)&ws.scratch));
+    CU(ws_get("blk_flags", sizeof(unsigned) * n, (void **)&ws.flags));
+    CU(ws_get("blk_nseg", sizeof(unsigned), (void **)&ws.nseg_dev));
+    CU(ws_get("blk_labels", sizeof(long long) * n, (void **)&g_block.labels));
+    CU(vb_block_split(de, dn, n, dce, n_east, dcn, n_north, ws, g_block.labels, st));
+    unsigned nseg = 0;
+    CU(cudaMemcpyAsync(&nseg, ws.nseg_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(ws_get("blk_seg_start", sizeof(unsigned) * ((size_t)nseg + 1), (void **)&ws.seg_start));
+    CU(ws_get("blk_seg_label", sizeof(long long) * (size_t)nseg, (void **)&ws.seg_label));
+    CU(vb_block_heads(n, nseg, ws, st));
+    if (labels) CU(cudaMemcpyAsync(labels, g_block.labels, sizeof(long long) * n, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    g_block.open = true;
+    g_block.n = n;
+    g_block.nseg = nseg;
+    *n_blocks = nseg;
+    return 0;
+}
+
+int vb200_block_ids(int64_t *ids)
+{
+    if (!g_block.open) return fail(VB200_E_BADARG, "vb200_block_split was not called");
+    if (g_block.nseg == 0) return 0;
+    if (!ids) return fail(VB200_E_BADARG, "null pointer");
+    CU(cudaMemcpy(ids, g_block.ws.seg_label, sizeof(long long) * g_block.nseg, cudaMemcpyDefault));
+    return 0;
+}
+
+int vb200_block_aggregate(const double *values, const double *weights, int64_t n, int32_t op, double *out)
+{
+    if (!g_block.open) return fail(VB200_E_BADARG, "vb200_block_split was not called");
+    if (n != g_block.n) return fail(VB200_E_BADARG, "values must have one entry per point of the last vb200_block_split (%lld given, %lld expected)", (long long)n, g_block.n);
+    if (op < VB_REDUCE_MEAN || op > VB_REDUCE_INV_SUM_W) return fail(VB200_E_BADARG, "unknown reduction %d", (int)op);
+    if (g_block.nseg == 0) return 0;
+    const bool needs_w = op == VB_REDUCE_WMEAN || op == VB_REDUCE_WVAR || op == VB_REDUCE_INV_SUM_W;
+    const bool needs_v = op != VB_REDUCE_COUNT && op != VB_REDUCE_INV_SUM_W;
+    if (!out || (needs_v && !values) || (needs_w && !weights)) return fail(VB200_E_BADARG, "null pointer");
+    cudaStream_t st = 0;
+    const double *dv = nullptr, *dw = nullptr;
+    if (needs_v) CU(stage_in("in_d", values, n, &dv, st));
+    if (needs_w) CU(stage_in("in_w", weights, n, &dw, st));
+    VbBlockWorkspace &ws = g_block.ws;
+    if (op == VB_REDUCE_MEDIAN) {
+        CU(ws_get("blk_mkeys0", sizeof(uint64_t) * n, (void **)&ws.mkeys[0]));
+        CU(ws_get("blk_mkeys1", sizeof(uint64_t) * n, (void **)&ws.mkeys[1]));
+        CU(ws_get("blk_mvals0", sizeof(unsigned) * n, (void **)&ws.mvals[0]));
+        CU(ws_get("blk_mvals1", sizeof(unsigned) * n, (void **)&ws.mvals[1]));
+    }
+    OutBuf ob;
+    CU(stage_out("blk_out", out, g_block.nseg, &ob));
+    CU(vb_block_aggregate(dv, dw, n, g_block.nseg, op, g_block.labels, ws, ob.dev, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vb200_distance_mask(const double *data_east, const double *data_north, int64_t n, double maxdist,
+                        const double *east, const double *north, int64_t n_points, uint8_t *mask)
+{
+    if (n < 0 || n_points < 0) return fail(VB200_E_BADARG, "negative size");
+    if (n > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many data points (limit 2^31 - 1)");
+    if (n_points == 0) return 0;
+    if (!mask || !east || !north || (n > 0 && (!data_east || !data_north))) return fail(VB200_E_BADARG, "null pointer");
+    if (maxdist != maxdist) return fail(VB200_E_BADARG, "maxdist is NaN");
+    cudaStream_t st = 0;
+    const bool mask_on_device = is_device_ptr(mask);
+    unsigned char *dmask = mask;
+    if (!mask_on_device) CU(ws_get("mask_out", (size_t)n_points, (void **)&dmask));
+    if (n == 0) {
+        CU(cudaMemsetAsync(dmask, 0, (size_t)n_points, st));
+    } else {
+        const double *de, *dn, *qe, *qn;
+        CU(stage_in("in_fe", data_east, n, &de, st));
+        CU(stage_in("in_fn", data_north, n, &dn, st));
+        CU(stage_in("in_e", east, n_points, &qe, st));
+        CU(stage_in("in_n", north, n_points, &qn, st));
+        // bounding box of the data -> uniform cell grid of pitch >= maxdist, at most 4096 x 4096 cells
+        const int parts = 512;
+        double *d_bbox, h_bbox[4 * 512];
+        CU(ws_get("mask_bbox", sizeof(double) * 4 * parts, (void **)&d_bbox));
+        vb_bbox_partial_kernel<<<parts, 256, 0, st>>>(de, dn, n, d_bbox);
+        ++vb_launch_counter;
+        CU(cudaMemcpyAsync(h_bbox, d_bbox, sizeof(h_bbox), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        double xmin = h_bbox[0], xmax = h_bbox[1], ymin = h_bbox[2], ymax = h_bbox[3];
+        for (int p = 1; p < parts; ++p) {
+            xmin = h_bbox[4 * p] < xmin ? h_bbox[4 * p] : xmin;
+            xmax = h_bbox[4 * p + 1] > xmax ? h_bbox[4 * p + 1] : xmax;
+            ymin = h_bbox[4 * p + 2] < ymin ? h_bbox[4 * p + 2] : ymin;
+            ymax = h_bbox[4 * p + 3] > ymax ? h_bbox[4 * p + 3] : ymax;
+        }
+        if (!(xmax >= xmin) || !(ymax >= ymin) || !(xmax - xmin < 1e300) || !(ymax - ymin < 1e300))
+            return fail(VB200_E_BADARG, "data coordinates must be finite");
+        const double extent = (xmax - xmin) > (ymax - ymin) ? (xmax - xmin) : (ymax - ymin);
+        double pitch = maxdist > 0.0 ? maxdist : 0.0;
+        if (pitch < extent / 4096.0) pitch = extent / 4096.0;
+        if (!(pitch > 0.0) || !(pitch < 1e300)) pitch = 1.0;
+        const int nx = (int)((xmax - xmin) / pitch) + 1, ny = (int)((ymax - ymin) / pitch) + 1;
+        const long long ncell = (long long)nx * ny;
+        unsigned *cell_of, *cell_start, *cursor, *scratch;
+        double *sorted_xy;
+        CU(ws_get("mask_cell_of", sizeof(unsigned) * n, (void **)&cell_of));
+        CU(ws_get("mask_cell_start", sizeof(unsigned) * (ncell + 1), (void **)&cell_start));
+        CU(ws_get("mask_cursor", sizeof(unsigned) * ncell, (void **)&cursor));
+        CU(ws_get("mask_scratch", sizeof(unsigned) * (vb_block_scan_scratch_elems(ncell + 1) + 16), (void **)&scratch));
+        CU(ws_get("mask_sorted_xy", sizeof(double) * 2 * n, (void **)&sorted_xy));
+        CU(vb_distance_mask(de, dn, n, xmin, ymin, pitch, nx, ny, cell_of, cell_start, cursor, scratch, sorted_xy, qe, qn,
+                            n_points, maxdist, dmask, st));
+    }
+    if (!mask_on_device) CU(cudaMemcpyAsync(mask, dmask, (size_t)n_points, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int64_t vb200_padded_cols(int64_t cols) { return (cols + VB_TILE - 1) / VB_TILE * VB_TILE; }
 
 int vb200_gram_factor(double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,

@@ -127,3 +127,42 @@ cudaError_t vb_launch_scale_system_batched(const double *G, int T, long long col
                                            const double *dampings_dev, int batch, double *L,
                                            long long stride, cudaStream_t stream);
 extern int vb_solve_variant;
+
+// ---- block reductions and the distance mask (vb_block.cu) --------------------------------------
+// reduction codes of vb200_block_aggregate (mirrored in include/verde_b200.h)
+#define VB_REDUCE_MEAN 0
+#define VB_REDUCE_SUM 1
+#define VB_REDUCE_MIN 2
+#define VB_REDUCE_MAX 3
+#define VB_REDUCE_COUNT 4
+#define VB_REDUCE_MEDIAN 5
+#define VB_REDUCE_VAR 6        // sample variance, ddof = 1 (pandas "var")
+#define VB_REDUCE_WMEAN 7      // sum(w v) / sum(w)          (numpy.average(values, weights=w))
+#define VB_REDUCE_WVAR 8       // sum(w (v - wmean)^2) / sum(w)
+#define VB_REDUCE_INV_SUM_W 9  // 1 / sum(w)                 (propagated uncertainty of a weighted mean)
+
+struct VbBlockWorkspace {
+    unsigned long long *keys[2];   // (label, point index) pairs, ping-pong
+    unsigned *vals[2];
+    unsigned long long *mkeys[2];  // second pair of buffers for the (label, value) order of the median
+    unsigned *mvals[2];
+    unsigned *counts;              // 256 x sort tiles
+    unsigned *scratch;             // scan scratch
+    unsigned *flags;               // n
+    unsigned *seg_start;           // nseg + 1
+    long long *seg_label;          // nseg
+    unsigned *nseg_dev;            // 1
+    int sorted;                    // which of keys/vals holds the label-sorted order
+    int label_bits;
+};
+long long vb_block_scan_scratch_elems(long long n);
+cudaError_t vb_block_split(const double *east, const double *north, long long n, const double *ce, int n_east,
+                           const double *cn, int n_north, VbBlockWorkspace &ws, long long *labels_dev,
+                           cudaStream_t st);
+cudaError_t vb_block_heads(long long n, long long nseg, VbBlockWorkspace &ws, cudaStream_t st);
+cudaError_t vb_block_aggregate(const double *values, const double *weights, long long n, long long nseg, int op,
+                               const long long *labels_dev, VbBlockWorkspace &ws, double *out, cudaStream_t st);
+cudaError_t vb_distance_mask(const double *data_e, const double *data_n, long long n, double x0, double y0,
+                             double pitch, int nx, int ny, unsigned *cell_of, unsigned *cell_start,
+                             unsigned *cursor, unsigned *scratch, double *sorted_xy, const double *qe,
+                             const double *qn, long long nq, double maxdist, unsigned char *mask, cudaStream_t st);
