@@ -124,3 +124,22 @@ def test_batched_sweep_reports_a_non_positive_definite_member(env):
     system.gram.mul_(-1.0)  # -G - tiny*I is negative definite, -G + huge*I is fine
     with pytest.raises(np.linalg.LinAlgError):
         system.solve_multi(e.size, [1e-30, 1e30])
+
+
+@pytest.mark.parametrize("mindist", [0.0, 1e-5])
+def test_wide_predict_kernel_is_bit_identical(env, mindist):
+    """predict_wide = 1: 512-thread CTAs with the conflict-free 8-copy log table; the lanes split the forces
+    exactly as in the default kernel, so the sums are the same bits."""
+    vb, kernels, lib = env
+    rng = np.random.RandomState(21)
+    npts, m = 80_000, 3000  # large enough for the 8-points-per-warp path the wide kernel replaces
+    e, nn = rng.uniform(0, 5000, npts), rng.uniform(-5000, 0, npts)
+    fe, fn, f = rng.uniform(0, 5000, m), rng.uniform(-5000, 0, m), rng.normal(size=m)
+    outs = []
+    try:
+        for wide in (0.0, 1.0):
+            assert lib.vb200_set_option(b"predict_wide", wide) == 0
+            outs.append(kernels.predict_b200(e, nn, fe, fn, mindist, f, np.empty(npts)).copy())
+    finally:
+        lib.vb200_set_option(b"predict_wide", 0.0)
+    np.testing.assert_array_equal(outs[0], outs[1])

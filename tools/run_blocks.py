@@ -37,7 +37,7 @@ def timed(fn, reps=5):
     return best
 
 
-for n, shape in ((400_000, (224, 224)), (20_000_000, (224, 224)), (20_000_000, (2000, 2000))):
+for n, shape in ((400_000, (224, 224)), (20_000_000, (224, 224)), (20_000_000, (2000, 2000)), (20_000_000, (8, 8))):
     rng = np.random.RandomState(0)
     e, nn, d = rng.uniform(0, 5000, n), rng.uniform(-5000, 0, n), rng.normal(size=n)
     ce = np.linspace(0, 5000, shape[1] + 1); ce = ce[:-1] + (ce[1] - ce[0]) / 2

@@ -323,6 +323,7 @@ int vb200_set_option(const char *key, double value)
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
     else if (k == "predict_minb") vb_predict_minb = (int)value;
     else if (k == "predict_pts") vb_predict_pts = (int)value;
+    else if (k == "predict_wide") vb_predict_wide = value != 0.0;
     else return fail(VB200_E_BADARG, "unknown option '%s'", key);
     return 0;
 }
@@ -936,6 +937,7 @@ int vb200_block_split(const double *east, const double *north, int64_t n, const 
     g_block.open = false;
     if (n < 0 || n_east < 1 || n_north < 1) return fail(VB200_E_BADARG, "bad sizes");
     if (n > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many points (limit 2^31 - 1)");
+    if ((long long)n_east * n_north > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many blocks (limit 2^31 - 1)");
     if (!n_blocks || !centers_east || !centers_north || (n > 0 && (!east || !north))) return fail(VB200_E_BADARG, "null pointer");
     cudaStream_t st = 0;
     if (n == 0) {

@@ -9,7 +9,7 @@
 // Both are HBM-bound integer / byte work (no tensor cores): the design rules are coalesced streams,
 // shared-memory staging of the per-CTA histograms and grids sized in multiples of the SM count.
 //
-//   block_split      label kernel (nearest centre per axis, 16 B in / 12 B out per point)
+//   block_split      label kernel (nearest centre per axis, 16 B in / 16 B out per point)
 //                    -> stable LSD radix sort of (label, point index) pairs, 8 bits per pass, only the
 //                       passes the label range needs (2 passes for 224 x 224 blocks)
 //                    -> segment heads by a flag + exclusive scan (no dense per-block array: a
@@ -122,12 +122,15 @@ cudaError_t scan_u32(unsigned *data, long long n, unsigned *scratch, unsigned *t
 }
 
 // ------------------------------------------------------------------------------------------
-// stable LSD radix sort of (uint64 key, uint32 payload) pairs, 8 bits per pass
+// stable LSD radix sort of (key, uint32 payload) pairs, 8 bits per pass; KeyT = uint32 (block
+// labels) or uint64 (order-preserving image of a double, for the median)
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS, RS_BINS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32, RS_WARP_ELEMS = RS_TILE / RS_WARPS;
 
+template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
-vb_rsort_hist_kernel(const uint64_t *__restrict__ keys, long long n, int shift, unsigned *__restrict__ counts,
+vb_rsort_hist_kernel(const KeyT *__restrict__ keys, long long n, int shift, unsigned *__restrict__ counts,
                      long long ntiles)
 {
     __shared__ unsigned h[RS_BINS];
@@ -143,57 +146,69 @@ vb_rsort_hist_kernel(const uint64_t *__restrict__ keys, long long n, int shift, 
     counts[(long long)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];  // digit-major
 }
 
+// Stable scatter of one 2048-element tile.  Warp w owns elements [256 w, 256 (w+1)) of the tile and ranks
+// them against its OWN digit counters (8 rounds of 32 consecutive elements, __match_any_sync inside a
+// round), so the ranking loop needs no CTA-wide barrier; one barrier pair turns the per-warp counts into
+// exclusive bases (digit d = thread d: prefix over the 8 warps on top of the tile's global offset).
+template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
-vb_rsort_scatter_kernel(const uint64_t *__restrict__ keys, const unsigned *__restrict__ vals, long long n, int shift,
-                        const unsigned *__restrict__ offsets, long long ntiles, uint64_t *__restrict__ keys_out,
+vb_rsort_scatter_kernel(const KeyT *__restrict__ keys, const unsigned *__restrict__ vals, long long n, int shift,
+                        const unsigned *__restrict__ offsets, long long ntiles, KeyT *__restrict__ keys_out,
                         unsigned *__restrict__ vals_out)
 {
-    __shared__ unsigned running[RS_BINS];               // elements of each digit already placed by this CTA
-    __shared__ unsigned warp_cnt[RS_THREADS / 32][RS_BINS + 1];
+    __shared__ unsigned cnt[RS_WARPS][RS_BINS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    running[threadIdx.x] = offsets[(long long)threadIdx.x * ntiles + blockIdx.x];
-    const long long base = (long long)blockIdx.x * RS_TILE;
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        for (int k = threadIdx.x; k < (RS_THREADS / 32) * (RS_BINS + 1); k += RS_THREADS) (&warp_cnt[0][0])[k] = 0;
-        __syncthreads();
-        const long long i = base + r * RS_THREADS + threadIdx.x;
-        const bool ok = i < n;
-        const uint64_t key = ok ? keys[i] : 0;
-        const unsigned val = ok ? vals[i] : 0;
-        const unsigned digit = ok ? ((unsigned)(key >> shift) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        const unsigned before = __popc(peers & ((1u << lane) - 1u));
-        if (before == 0) warp_cnt[warp][digit] = __popc(peers);
-        __syncthreads();
-        // digit d (thread d): exclusive prefix over the 8 warps, on top of what earlier rounds placed
-        {
-            unsigned run = running[threadIdx.x];
 #pragma unroll
-            for (int w = 0; w < RS_THREADS / 32; ++w) {
-                const unsigned t = warp_cnt[w][threadIdx.x];
-                warp_cnt[w][threadIdx.x] = run;
-                run += t;
-            }
-            running[threadIdx.x] = run;
+    for (int w = 0; w < RS_WARPS; ++w) cnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const long long wbase = (long long)blockIdx.x * RS_TILE + warp * RS_WARP_ELEMS;
+    KeyT key[RS_ITEMS];
+    unsigned val[RS_ITEMS], rank[RS_ITEMS], digit[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys[i] : (KeyT)0;
+        val[r] = ok ? vals[i] : 0u;
+        digit[r] = ok ? ((unsigned)(key[r] >> shift) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit[r]);
+        const unsigned before = __popc(peers & ((1u << lane) - 1u));
+        const unsigned seen = ok ? cnt[warp][digit[r]] : 0u;
+        __syncwarp();
+        if (ok && before == 0) cnt[warp][digit[r]] = seen + __popc(peers);
+        __syncwarp();
+        rank[r] = seen + before;
+    }
+    __syncthreads();
+    {
+        unsigned run = offsets[(long long)threadIdx.x * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const unsigned t = cnt[w][threadIdx.x];
+            cnt[w][threadIdx.x] = run;
+            run += t;
         }
-        __syncthreads();
-        if (ok) {
-            const unsigned pos = warp_cnt[warp][digit] + before;
-            keys_out[pos] = key;
-            vals_out[pos] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        if (digit[r] < 256u) {
+            const unsigned pos = cnt[warp][digit[r]] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
         }
-        __syncthreads();
     }
 }
 
 struct SortBuffers {
-    uint64_t *keys[2];
+    void *keys[2];      // n keys each (allocated for uint64)
     unsigned *vals[2];
     unsigned *counts;   // 256 * ntiles
     unsigned *scratch;  // scan scratch
 };
 
 // sorts on bits [0, nbits) rounded up to whole bytes; result ends in buffers[*which]
+template <typename KeyT>
 cudaError_t radix_sort_pairs(SortBuffers &b, long long n, int nbits, int *which, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
@@ -201,12 +216,13 @@ cudaError_t radix_sort_pairs(SortBuffers &b, long long n, int nbits, int *which,
     const int passes = (nbits + 7) / 8;
     int cur = *which;
     for (int p = 0; p < passes; ++p) {
-        vb_rsort_hist_kernel<<<(unsigned)ntiles, RS_THREADS, 0, st>>>(b.keys[cur], n, 8 * p, b.counts, ntiles);
+        vb_rsort_hist_kernel<KeyT><<<(unsigned)ntiles, RS_THREADS, 0, st>>>((const KeyT *)b.keys[cur], n, 8 * p, b.counts, ntiles);
         ++vb_launch_counter;
         cudaError_t e = scan_u32(b.counts, (long long)RS_BINS * ntiles, b.scratch, nullptr, st);
         if (e != cudaSuccess) return e;
-        vb_rsort_scatter_kernel<<<(unsigned)ntiles, RS_THREADS, 0, st>>>(b.keys[cur], b.vals[cur], n, 8 * p, b.counts, ntiles,
-                                                                        b.keys[cur ^ 1], b.vals[cur ^ 1]);
+        vb_rsort_scatter_kernel<KeyT><<<(unsigned)ntiles, RS_THREADS, 0, st>>>((const KeyT *)b.keys[cur], b.vals[cur], n, 8 * p,
+                                                                              b.counts, ntiles, (KeyT *)b.keys[cur ^ 1],
+                                                                              b.vals[cur ^ 1]);
         ++vb_launch_counter;
         cur ^= 1;
     }
@@ -233,20 +249,20 @@ __device__ __forceinline__ int nearest_centre(double x, const double *__restrict
 __global__ void __launch_bounds__(256)
 vb_block_label_kernel(const double *__restrict__ east, const double *__restrict__ north, long long n,
                       const double *__restrict__ ce, int n_east, const double *__restrict__ cn, int n_north,
-                      uint64_t *__restrict__ keys, unsigned *__restrict__ vals, long long *__restrict__ labels)
+                      unsigned *__restrict__ keys, unsigned *__restrict__ vals, long long *__restrict__ labels)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int je = nearest_centre(east[i], ce, n_east);
         const int jn = nearest_centre(north[i], cn, n_north);
         const long long label = (long long)jn * n_east + je;  // raveled C order of the (n_north, n_east) centre grid
-        keys[i] = (uint64_t)label;
+        keys[i] = (unsigned)label;  // n_east * n_north < 2^31 (checked by the caller)
         vals[i] = (unsigned)i;
         if (labels) labels[i] = label;
     }
 }
 
 __global__ void __launch_bounds__(256)
-vb_segment_flag_kernel(const uint64_t *__restrict__ sorted_keys, long long n, unsigned *__restrict__ flags)
+vb_segment_flag_kernel(const unsigned *__restrict__ sorted_keys, long long n, unsigned *__restrict__ flags)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) ? 1u : 0u;
@@ -254,7 +270,7 @@ vb_segment_flag_kernel(const uint64_t *__restrict__ sorted_keys, long long n, un
 
 // flags_scanned[i] = index of the segment that starts at i (valid where a head is)
 __global__ void __launch_bounds__(256)
-vb_segment_heads_kernel(const uint64_t *__restrict__ sorted_keys, const unsigned *__restrict__ scanned, long long n,
+vb_segment_heads_kernel(const unsigned *__restrict__ sorted_keys, const unsigned *__restrict__ scanned, long long n,
                         unsigned *__restrict__ seg_start, long long *__restrict__ seg_label, long long nseg)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,29 +315,63 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
+// GROUP = 32: one warp per block (the usual case, a handful of points per block);
+// GROUP = 256: one CTA per block, for block grids so coarse that a block holds thousands of points.
+// Both reduce in a fixed order (lane-strided compensated partial sums, shuffle tree, then the 8 warp
+// totals in warp order), so results do not depend on scheduling.
+template <int GROUP>
+__device__ __forceinline__ double group_sum(double v, double *sh)
+{
+    v = warp_sum(v);
+    if (GROUP == 32) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    return t;
+}
+template <int GROUP>
+__device__ __forceinline__ double group_minmax(double v, bool is_min, double *sh)
+{
+    v = is_min ? warp_min(v) : warp_max(v);
+    if (GROUP == 32) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = sh[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = is_min ? fmin(t, sh[w]) : fmax(t, sh[w]);
+    return t;
+}
+
+template <int GROUP>
 __global__ void __launch_bounds__(256)
 vb_block_aggregate_kernel(const unsigned *__restrict__ perm, const unsigned *__restrict__ seg_start, long long nseg,
                           const double *__restrict__ v, const double *__restrict__ w, int op, double *__restrict__ out)
 {
-    const long long seg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (seg >= nseg) return;
+    __shared__ double sh[8];
+    const long long seg = GROUP == 32 ? (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (long long)blockIdx.x;
+    const int lane = GROUP == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    if (seg >= nseg) return;  // whole warps (GROUP 32) or whole CTAs (GROUP 256) leave together
     const unsigned a = seg_start[seg], b = seg_start[seg + 1];
     const double cnt = (double)(b - a);
     double res = 0.0;
     if (op == VB_REDUCE_COUNT) {
         res = cnt;
     } else if (op == VB_REDUCE_MIN || op == VB_REDUCE_MAX) {
-        double m = (op == VB_REDUCE_MIN) ? 1.0 / 0.0 : -1.0 / 0.0;
-        bool nan = false;
-        for (unsigned k = a + lane; k < b; k += 32) {
+        const bool is_min = op == VB_REDUCE_MIN;
+        double m = is_min ? 1.0 / 0.0 : -1.0 / 0.0;
+        double nan = 0.0;
+        for (unsigned k = a + lane; k < b; k += GROUP) {
             const double x = v[perm[k]];
-            nan |= (x != x);
-            m = (op == VB_REDUCE_MIN) ? fmin(m, x) : fmax(m, x);
+            if (x != x) nan = 1.0;
+            m = is_min ? fmin(m, x) : fmax(m, x);
         }
-        m = (op == VB_REDUCE_MIN) ? warp_min(m) : warp_max(m);
-        nan = __any_sync(0xffffffffu, nan);
-        res = nan ? (0.0 / 0.0) : m;  // numpy's min/max propagate NaN
+        m = group_minmax<GROUP>(m, is_min, sh);
+        nan = group_minmax<GROUP>(nan, false, sh);
+        res = nan > 0.0 ? (0.0 / 0.0) : m;  // numpy's min/max propagate NaN
     } else if (op == VB_REDUCE_MEDIAN) {
         // perm is sorted by (block, value) for this op
         const unsigned len = b - a;
@@ -332,7 +382,7 @@ vb_block_aggregate_kernel(const unsigned *__restrict__ perm, const unsigned *__r
         // sums: SUM, MEAN, WMEAN, VAR (ddof = 1), WVAR, INV_SUM_W
         const bool weighted = (op == VB_REDUCE_WMEAN || op == VB_REDUCE_WVAR);
         Kahan sv, sw;
-        for (unsigned k = a + lane; k < b; k += 32) {
+        for (unsigned k = a + lane; k < b; k += GROUP) {
             const unsigned i = perm[k];
             if (op == VB_REDUCE_INV_SUM_W) {
                 sw.add(w[i]);
@@ -344,8 +394,8 @@ vb_block_aggregate_kernel(const unsigned *__restrict__ perm, const unsigned *__r
                 sv.add(v[i]);
             }
         }
-        const double tv = warp_sum(sv.value());
-        const double tw = warp_sum(sw.value());
+        const double tv = group_sum<GROUP>(sv.value(), sh);
+        const double tw = group_sum<GROUP>(sw.value(), sh);
         if (op == VB_REDUCE_SUM) res = tv;
         else if (op == VB_REDUCE_INV_SUM_W) res = 1.0 / tw;
         else {
@@ -354,12 +404,12 @@ vb_block_aggregate_kernel(const unsigned *__restrict__ perm, const unsigned *__r
                 res = mean;
             } else {
                 Kahan s2;
-                for (unsigned k = a + lane; k < b; k += 32) {
+                for (unsigned k = a + lane; k < b; k += GROUP) {
                     const unsigned i = perm[k];
                     const double dlt = v[i] - mean;
                     s2.add(weighted ? w[i] * dlt * dlt : dlt * dlt);
                 }
-                const double t2 = warp_sum(s2.value());
+                const double t2 = group_sum<GROUP>(s2.value(), sh);
                 res = weighted ? t2 / tw : t2 / (cnt - 1.0);  // pandas var: ddof = 1 (NaN for single points)
             }
         }
@@ -383,10 +433,10 @@ vb_value_keys_kernel(const double *__restrict__ v, long long n, uint64_t *__rest
 
 __global__ void __launch_bounds__(256)
 vb_label_keys_kernel(const long long *__restrict__ labels, const unsigned *__restrict__ vals, long long n,
-                     uint64_t *__restrict__ keys)
+                     unsigned *__restrict__ keys)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = (uint64_t)labels[vals[i]];
+    if (i < n) keys[i] = (unsigned)labels[vals[i]];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -478,20 +528,20 @@ cudaError_t vb_block_split(const double *east, const double *north, long long n,
                            const double *cn, int n_north, VbBlockWorkspace &ws, long long *labels_dev,
                            cudaStream_t st)
 {
-    SortBuffers sb = {{(uint64_t *)ws.keys[0], (uint64_t *)ws.keys[1]}, {ws.vals[0], ws.vals[1]}, ws.counts, ws.scratch};
-    vb_block_label_kernel<<<grid_for(n), 256, 0, st>>>(east, north, n, ce, n_east, cn, n_north, sb.keys[0], sb.vals[0],
-                                                       labels_dev);
+    SortBuffers sb = {{ws.keys[0], ws.keys[1]}, {ws.vals[0], ws.vals[1]}, ws.counts, ws.scratch};
+    vb_block_label_kernel<<<grid_for(n), 256, 0, st>>>(east, north, n, ce, n_east, cn, n_north, (unsigned *)sb.keys[0],
+                                                       sb.vals[0], labels_dev);
     ++vb_launch_counter;
     int nbits = 1;
-    while (nbits < 62 && (1LL << nbits) < (long long)n_east * n_north) ++nbits;
+    while (nbits < 31 && (1LL << nbits) < (long long)n_east * n_north) ++nbits;
     int which = 0;
-    cudaError_t e = radix_sort_pairs(sb, n, nbits, &which, st);
+    cudaError_t e = radix_sort_pairs<unsigned>(sb, n, nbits, &which, st);
     if (e != cudaSuccess) return e;
     ws.sorted = which;
     ws.label_bits = nbits;
     // segment heads
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    vb_segment_flag_kernel<<<blocks, 256, 0, st>>>(sb.keys[which], n, ws.flags);
+    vb_segment_flag_kernel<<<blocks, 256, 0, st>>>((const unsigned *)sb.keys[which], n, ws.flags);
     ++vb_launch_counter;
     return scan_u32(ws.flags, n, ws.scratch, ws.nseg_dev, st);
 }
@@ -499,7 +549,7 @@ cudaError_t vb_block_split(const double *east, const double *north, long long n,
 cudaError_t vb_block_heads(long long n, long long nseg, VbBlockWorkspace &ws, cudaStream_t st)
 {
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    vb_segment_heads_kernel<<<blocks, 256, 0, st>>>((const uint64_t *)ws.keys[ws.sorted], ws.flags, n, ws.seg_start, ws.seg_label, nseg);
+    vb_segment_heads_kernel<<<blocks, 256, 0, st>>>((const unsigned *)ws.keys[ws.sorted], ws.flags, n, ws.seg_start, ws.seg_label, nseg);
     ++vb_launch_counter;
     return cudaGetLastError();
 }
@@ -510,22 +560,27 @@ cudaError_t vb_block_aggregate(const double *values, const double *weights, long
     const unsigned *perm = ws.vals[ws.sorted];
     if (op == VB_REDUCE_MEDIAN) {
         // (block, value) order: value pass first, stable block pass second, in the spare buffers
-        SortBuffers sb = {{(uint64_t *)ws.mkeys[0], (uint64_t *)ws.mkeys[1]}, {ws.mvals[0], ws.mvals[1]}, ws.counts, ws.scratch};
+        SortBuffers sb = {{ws.mkeys[0], ws.mkeys[1]}, {ws.mvals[0], ws.mvals[1]}, ws.counts, ws.scratch};
         const unsigned blocks = (unsigned)((n + 255) / 256);
-        vb_value_keys_kernel<<<blocks, 256, 0, st>>>(values, n, sb.keys[0], sb.vals[0]);
+        vb_value_keys_kernel<<<blocks, 256, 0, st>>>(values, n, (uint64_t *)sb.keys[0], sb.vals[0]);
         ++vb_launch_counter;
         int which = 0;
-        cudaError_t e = radix_sort_pairs(sb, n, 64, &which, st);
+        cudaError_t e = radix_sort_pairs<uint64_t>(sb, n, 64, &which, st);
         if (e != cudaSuccess) return e;
-        vb_label_keys_kernel<<<blocks, 256, 0, st>>>(labels_dev, sb.vals[which], n, sb.keys[which]);
+        // the value keys are spent: the same buffer now takes the 32-bit block labels in value order
+        vb_label_keys_kernel<<<blocks, 256, 0, st>>>(labels_dev, sb.vals[which], n, (unsigned *)sb.keys[which]);
         ++vb_launch_counter;
-        e = radix_sort_pairs(sb, n, ws.label_bits, &which, st);
+        e = radix_sort_pairs<unsigned>(sb, n, ws.label_bits, &which, st);
         if (e != cudaSuccess) return e;
         perm = sb.vals[which];
     }
-    const long long threads = nseg * 32;
-    vb_block_aggregate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(perm, ws.seg_start, nseg, values, weights,
-                                                                                op, out);
+    if (n / nseg >= 2048) {
+        vb_block_aggregate_kernel<256><<<(unsigned)nseg, 256, 0, st>>>(perm, ws.seg_start, nseg, values, weights, op, out);
+    } else {
+        const long long threads = nseg * 32;
+        vb_block_aggregate_kernel<32><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(perm, ws.seg_start, nseg, values,
+                                                                                        weights, op, out);
+    }
     ++vb_launch_counter;
     return cudaGetLastError();
 }

@@ -98,12 +98,13 @@ __device__ __forceinline__ void vb_logtab_stage(double *smem_tab, const double2 
 template <int REP = 1>
 __device__ __forceinline__ double vb_log_fast(double d, const double2 *tab)
 {
-    static_assert(REP == 1 || REP == 2 || REP == 4, "replication factor");
+    static_assert(REP == 1 || REP == 2 || REP == 4 || REP == 8, "replication factor");
     const int hi = __double2hiint(d);
     const int lo = __double2loint(d);
     // byte offset of table entry idx = mantissa bits 19..10: idx * 16 * REP (tab already points at
     // this lane's copy)
-    const int off = REP == 1 ? ((hi >> 6) & 0x3FF0) : REP == 2 ? ((hi >> 5) & 0x7FE0) : ((hi >> 4) & 0xFFC0);
+    const int off = REP == 1 ? ((hi >> 6) & 0x3FF0) : REP == 2 ? ((hi >> 5) & 0x7FE0) : REP == 4 ? ((hi >> 4) & 0xFFC0)
+                                                                                                  : ((hi >> 3) & 0x1FF80);
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
     // double(biased exponent - 1023) without an I2F: 2^52 + biased as a bit pattern
     const double ed = __hiloint2double(0x43300000, (unsigned)hi >> 20) - 4503599627371519.0;

@@ -62,26 +62,31 @@ constexpr int PRED_TAB_BYTES = VB_LOGTAB_ENTRIES * 16 * PRED_TAB_REP;
 constexpr int PRED2_CHUNK = 512;  // 2-D kernel stages 4 arrays; static smem limit is 48 KB
 
 // MODE 0: fast Green's, mindist == 0; MODE 1: fast, mindist != 0; MODE 2: exact.
-template <int PTS, int MODE, int MINB>
-__global__ void __launch_bounds__(PRED_THREADS, MINB)
+// THREADS / REP: 256 threads with 4 interleaved table copies (64 KB, two CTAs per SM), or the "wide" flavour
+// 512 threads with 8 copies (128 KB, one CTA per SM): copy c = lane % 8 of entry idx sits at double2 index
+// idx*8 + c, i.e. in banks 4c..4c+3 whatever idx is, so the 8 lanes of every LDS.128 quarter-warp hit 8
+// disjoint bank groups: the data-dependent table lookup becomes bank-conflict free.
+template <int PTS, int MODE, int MINB, int THREADS = PRED_THREADS, int REP = PRED_TAB_REP>
+__global__ void __launch_bounds__(THREADS, MINB)
 vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ north, long long npts,
                   const double *__restrict__ fe, const double *__restrict__ fn,
                   const double *__restrict__ force, int m_begin_stride, int m_total,
                   double mindist, double *__restrict__ out)
 {
-    extern __shared__ __align__(16) double s_tab[];  // PRED_TAB_REP interleaved copies of the log table
+    extern __shared__ __align__(16) double s_tab[];  // REP interleaved copies of the log table
     __shared__ double s_fe[PRED_CHUNK], s_fn[PRED_CHUNK], s_f[PRED_CHUNK];
-    __shared__ double s_out[PRED_WARPS * PTS];
+    constexpr int WARPS = THREADS / 32;
+    __shared__ double s_out[WARPS * PTS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (MODE != 2) vb_logtab_stage<PRED_TAB_REP>(s_tab, vb_logtab_global);
-    const double2 *tab = reinterpret_cast<const double2 *>(s_tab) + (lane & (PRED_TAB_REP - 1));
+    if (MODE != 2) vb_logtab_stage<REP>(s_tab, vb_logtab_global);
+    const double2 *tab = reinterpret_cast<const double2 *>(s_tab) + (lane & (REP - 1));
 
     // force range of this split (blockIdx.y): [m0, m1)
     const int m0 = min(m_total, (int)blockIdx.y * m_begin_stride);
     const int m1 = min(m_total, m0 + m_begin_stride);
 
-    const long long p0 = ((long long)blockIdx.x * PRED_WARPS + warp) * PTS;
+    const long long p0 = ((long long)blockIdx.x * WARPS + warp) * PTS;
     double px[PTS], py[PTS], acc[PTS];
 #pragma unroll
     for (int p = 0; p < PTS; ++p) {
@@ -99,7 +104,7 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
         const int cn = min(PRED_CHUNK, m1 - c0);
         __syncthreads();
         int bad = 0;
-        for (int t = threadIdx.x; t < cn; t += PRED_THREADS) {
+        for (int t = threadIdx.x; t < cn; t += THREADS) {
             const double a = fe[c0 + t], b = fn[c0 + t], c = force[c0 + t];
             s_fe[t] = a;
             s_fn[t] = b;
@@ -113,8 +118,8 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
 #pragma unroll
             for (int p = 0; p < PTS; ++p) {
                 double g;
-                if (MODE == 0) g = vb_greens_fast<false, PRED_TAB_REP>(px[p] - fx, py[p] - fy, mindist, tab);
-                else if (MODE == 1) g = vb_greens_fast<true, PRED_TAB_REP>(px[p] - fx, py[p] - fy, mindist, tab);
+                if (MODE == 0) g = vb_greens_fast<false, REP>(px[p] - fx, py[p] - fy, mindist, tab);
+                else if (MODE == 1) g = vb_greens_fast<true, REP>(px[p] - fx, py[p] - fy, mindist, tab);
                 else g = vb_greens_exact(px[p] - fx, py[p] - fy, mindist);
                 acc[p] = fma(g, fc, acc[p]);
             }
@@ -129,10 +134,10 @@ vb_predict_kernel(const double *__restrict__ east, const double *__restrict__ no
         if (lane == 0) s_out[warp * PTS + p] = v;
     }
     __syncthreads();
-    // coalesced write of the CTA's PRED_WARPS*PTS consecutive points
-    const long long base = (long long)blockIdx.x * PRED_WARPS * PTS;
+    // coalesced write of the CTA's WARPS*PTS consecutive points
+    const long long base = (long long)blockIdx.x * WARPS * PTS;
     double *dst = out + (long long)blockIdx.y * npts;
-    for (int t = threadIdx.x; t < PRED_WARPS * PTS; t += PRED_THREADS) {
+    for (int t = threadIdx.x; t < WARPS * PTS; t += THREADS) {
         if (base + t < npts) dst[base + t] = s_out[t];
     }
 }
@@ -303,6 +308,7 @@ void vb_predict_plan(long long npts, long long m, int *pts, int *nsplit)
 
 int vb_predict_minb = 2;  // resident CTAs per SM the scalar predict kernel is compiled for (2..4)
 int vb_predict_pts = 0;   // 0 = choose from the problem size
+int vb_predict_wide = 0;  // 1: 512-thread CTAs with the conflict-free 8-copy log table for the large-problem path
 
 template <int PTS, int MINB>
 static cudaError_t launch_predict_pts_minb(int mode, dim3 grid, const double *e, const double *n,
@@ -352,6 +358,21 @@ cudaError_t vb_launch_predict(const double *e, const double *n, long long npts, 
     const int stride = (int)((m + nsplit - 1) / nsplit);
     dim3 grid((unsigned)((npts + (long long)PRED_WARPS * pts - 1) / ((long long)PRED_WARPS * pts)), nsplit);
     double *dst = nsplit > 1 ? scratch : out;
+    if (vb_predict_wide && pts == 8 && mode != 2) {
+        // large problems: one 512-thread CTA per SM with the conflict-free 8-copy table
+        constexpr int WT = 512, WREP = 8, WBYTES = VB_LOGTAB_ENTRIES * 16 * WREP;
+        dim3 wgrid((unsigned)((npts + (long long)(WT / 32) * 8 - 1) / ((long long)(WT / 32) * 8)), nsplit);
+        if (mode == 0) {
+            err = cudaFuncSetAttribute(vb_predict_kernel<8, 0, 1, WT, WREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, WBYTES);
+            if (err != cudaSuccess) return err;
+            vb_predict_kernel<8, 0, 1, WT, WREP><<<wgrid, WT, WBYTES, stream>>>(e, n, npts, fe, fn, f, stride, (int)m, mindist, dst);
+        } else {
+            err = cudaFuncSetAttribute(vb_predict_kernel<8, 1, 1, WT, WREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, WBYTES);
+            if (err != cudaSuccess) return err;
+            vb_predict_kernel<8, 1, 1, WT, WREP><<<wgrid, WT, WBYTES, stream>>>(e, n, npts, fe, fn, f, stride, (int)m, mindist, dst);
+        }
+        err = cudaGetLastError();
+    } else
     switch (pts) {
     case 8: err = launch_predict_pts<8>(mode, grid, e, n, npts, fe, fn, f, stride, (int)m, mindist, dst, stream); break;
     case 4: err = launch_predict_pts<4>(mode, grid, e, n, npts, fe, fn, f, stride, (int)m, mindist, dst, stream); break;

@@ -38,7 +38,7 @@ extern long long vb_launch_counter;
 // DMMA tile kernel flavour (see vb_gemm.cu)
 extern int vb_gemm_variant, vb_gemm_strip;
 // predict kernel tuning knobs (vb_greens.cu)
-extern int vb_predict_minb, vb_predict_pts;
+extern int vb_predict_minb, vb_predict_pts, vb_predict_wide;
 
 cudaError_t vb_init_tables();
 cudaError_t vb_launch_jacobian(const double *e, const double *n, long long npts, const double *fe,
@@ -142,9 +142,9 @@ extern int vb_solve_variant;
 #define VB_REDUCE_INV_SUM_W 9  // 1 / sum(w)                 (propagated uncertainty of a weighted mean)
 
 struct VbBlockWorkspace {
-    unsigned long long *keys[2];   // (label, point index) pairs, ping-pong
+    void *keys[2];                 // (label, point index) pairs, ping-pong (uint32 labels; sized for uint64)
     unsigned *vals[2];
-    unsigned long long *mkeys[2];  // second pair of buffers for the (label, value) order of the median
+    void *mkeys[2];                // second pair of buffers for the (label, value) order of the median
     unsigned *mvals[2];
     unsigned *counts;              // 256 x sort tiles
     unsigned *scratch;             // scan scratch
