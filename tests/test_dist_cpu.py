@@ -89,6 +89,9 @@ def _worker(rank, world, port, out_dir):
     dist.set_cholesky("replicated")
     assert not dist.use_distributed_cholesky(391, 8)
     dist.set_cholesky("auto")
+    # a status code seen by one rank only (failed pivot on the panel owner) becomes collective
+    assert dist.agree_on_status(7 if rank == 1 else 0) == (0, 7)
+    assert dist.agree_on_status(-2 if rank == 0 else 0) == (-2, 0)
     # 5. turning sharding off makes the helpers local again
     dist.set_sharding(False)
     assert not dist.sharding_active()

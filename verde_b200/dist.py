@@ -118,6 +118,26 @@ def broadcast_(tensor, src):
     return tensor
 
 
+def agree_on_status(code):
+    """
+    Make a per-rank status code collective: returns ``(lowest, highest)`` over all ranks, so that every
+    rank raises (or not) together.  A failed pivot is only seen by the rank that owns the panel.
+    """
+    import torch
+
+    rank, size = world()
+    if size == 1:
+        return int(code), int(code)
+    import torch.distributed as td
+
+    t = torch.tensor([-int(code), int(code)], dtype=torch.int64)
+    if td.get_backend() == "nccl":
+        t = t.cuda()
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    lo, hi = t.cpu().tolist()
+    return -int(lo), int(hi)
+
+
 def allreduce_sum_(tensor):
     "In-place sum over ranks of a torch tensor (NCCL for CUDA tensors, gloo for CPU)."
     import torch.distributed as td

@@ -277,7 +277,9 @@ class GramSystem:
         params = np.empty(cols, dtype=np.float64) if out is None else out  # host array or CUDA tensor
         rc = lib.vb200_chol_finish(gram_ptr, cols, _cabi.ptr(params), ctypes.byref(self.info))
         _remember(self.info)
-        _cabi.check(rc, "chol_finish")
+        # a non-positive pivot is only recorded on the rank that owns its panel: agree before raising
+        lowest, highest = dist.agree_on_status(rc)
+        _cabi.check(rc if rc != 0 else (lowest if lowest < 0 else highest), "chol_finish")
         return params
 
     def factor(self, total_rows, damping):
