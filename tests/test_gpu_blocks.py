@@ -202,5 +202,8 @@ def test_distance_mask_api(vb, g):
     coords = vb.grid_coordinates(sp.region_, shape=(30, 40))
     inside = vb.distance_mask((tab.easting.values, tab.northing.values), 300.0, coordinates=coords)
     assert np.isnan(values[~inside]).all() and np.isfinite(values[inside]).all()
+    # infinite / negative maxdist
+    assert vb.distance_mask((tab.easting.values, tab.northing.values), np.inf, coordinates=coords).all()
+    assert not vb.distance_mask((tab.easting.values, tab.northing.values), -1.0, coordinates=coords).any()
     # empty data: nothing is close
     assert not vb.distance_mask((np.array([]), np.array([])), 1.0, coordinates=coords).any()

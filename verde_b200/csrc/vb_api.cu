@@ -1031,6 +1031,8 @@ int vb200_distance_mask(const double *data_east, const double *data_north, int64
     if (!mask_on_device) CU(ws_get("mask_out", (size_t)n_points, (void **)&dmask));
     if (n == 0) {
         CU(cudaMemsetAsync(dmask, 0, (size_t)n_points, st));
+    } else if (maxdist >= 1e300) {
+        CU(cudaMemsetAsync(dmask, 1, (size_t)n_points, st));  // everything is within an infinite distance
     } else {
         const double *de, *dn, *qe, *qn;
         CU(stage_in("in_fe", data_east, n, &de, st));
