@@ -149,19 +149,27 @@ vb_rsort_hist_kernel(const KeyT *__restrict__ keys, long long n, int shift, unsi
 // Stable scatter of one 2048-element tile.  Warp w owns elements [256 w, 256 (w+1)) of the tile and ranks
 // them against its OWN digit counters (8 rounds of 32 consecutive elements, __match_any_sync inside a
 // round), so the ranking loop needs no CTA-wide barrier; one barrier pair turns the per-warp counts into
-// exclusive bases (digit d = thread d: prefix over the 8 warps on top of the tile's global offset).
+// exclusive bases (digit d = thread d: prefix over the 8 warps).  The tile is then re-ordered IN SHARED
+// MEMORY (position = start of its digit inside the tile + rank) and written out in tile order, so the
+// elements of one digit leave as one contiguous run: full 32-byte sectors instead of one sector per
+// element (ncu, 20M points: 30 sectors per store request before, profiles/r01_ncu_blocks_summary.json).
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS)
 vb_rsort_scatter_kernel(const KeyT *__restrict__ keys, const unsigned *__restrict__ vals, long long n, int shift,
                         const unsigned *__restrict__ offsets, long long ntiles, KeyT *__restrict__ keys_out,
                         unsigned *__restrict__ vals_out)
 {
-    __shared__ unsigned cnt[RS_WARPS][RS_BINS];
+    __shared__ unsigned cnt[RS_WARPS][RS_BINS];  // per-warp digit counts -> per-warp base inside the tile
+    __shared__ unsigned dig_delta[RS_BINS];      // global offset of the digit minus its tile start
+    __shared__ KeyT s_key[RS_TILE];
+    __shared__ unsigned s_val[RS_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) cnt[w][threadIdx.x] = 0;
     __syncthreads();
-    const long long wbase = (long long)blockIdx.x * RS_TILE + warp * RS_WARP_ELEMS;
+    const long long tile_base = (long long)blockIdx.x * RS_TILE;
+    const long long wbase = tile_base + warp * RS_WARP_ELEMS;
+    const int tile_n = (int)((n - tile_base < RS_TILE) ? (n - tile_base) : RS_TILE);
     KeyT key[RS_ITEMS];
     unsigned val[RS_ITEMS], rank[RS_ITEMS], digit[RS_ITEMS];
 #pragma unroll
@@ -180,8 +188,15 @@ vb_rsort_scatter_kernel(const KeyT *__restrict__ keys, const unsigned *__restric
         rank[r] = seen + before;
     }
     __syncthreads();
+    // digit d = thread d: total of the digit in this tile, exclusive scan over digits, per-warp bases
     {
-        unsigned run = offsets[(long long)threadIdx.x * ntiles + blockIdx.x];
+        unsigned total = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) total += cnt[w][threadIdx.x];
+        unsigned dummy;
+        const unsigned start = cta_exclusive_scan(total, &dummy);
+        dig_delta[threadIdx.x] = offsets[(long long)threadIdx.x * ntiles + blockIdx.x] - start;
+        unsigned run = start;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const unsigned t = cnt[w][threadIdx.x];
@@ -194,9 +209,16 @@ vb_rsort_scatter_kernel(const KeyT *__restrict__ keys, const unsigned *__restric
     for (int r = 0; r < RS_ITEMS; ++r) {
         if (digit[r] < 256u) {
             const unsigned pos = cnt[warp][digit[r]] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            s_key[pos] = key[r];
+            s_val[pos] = val[r];
         }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tile_n; t += RS_THREADS) {
+        const KeyT k = s_key[t];
+        const unsigned pos = t + dig_delta[(unsigned)(k >> shift) & 255u];
+        keys_out[pos] = k;
+        vals_out[pos] = s_val[t];
     }
 }
 
