@@ -61,7 +61,8 @@ int vb200_device_count(void);
 int vb200_set_device(int device);
 /* tunables: "predict_exact" (0/1), "chol_panel_tiles" (1..16), "gram_slab_chunks" (1..16),
  * "gram_fused" (0/1: generate Jacobian rows in shared memory inside the Gram kernel instead of staging
- * a panel), "gemm_variant" (0/1/2/3), "gemm_strip", "predict_pts", "predict_minb" */
+ * a panel), "gemm_variant" (0/1/2/3), "gemm_strip", "predict_pts", "predict_minb", "predict_wide" (0/1),
+ * "sweep_group" (systems per batch of vb200_gram_solve_multi, 0 = as many as fit), "solve_variant" */
 int vb200_set_option(const char *key, double value);
 /* frees the cached device workspace (Gram matrix, panels) */
 int vb200_release_workspace(void);

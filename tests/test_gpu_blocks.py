@@ -207,3 +207,30 @@ def test_distance_mask_api(vb, g):
     assert not vb.distance_mask((tab.easting.values, tab.northing.values), -1.0, coordinates=coords).any()
     # empty data: nothing is close
     assert not vb.distance_mask((np.array([]), np.array([])), 1.0, coordinates=coords).any()
+
+
+def test_gallery_pipeline_blockreduce_spline_mask(vb, bo):
+    """doc/gallery_src/spline.py: Chain([BlockReduce(mean), Spline(damping)]) -> grid -> distance_mask, every
+    numeric step on the device; checked against the same steps done one by one with the CPU oracles."""
+    import verde_oracle as vo
+
+    tab = vb.CheckerBoard(region=(0, 5000, -5000, 0)).scatter(size=6000, random_state=2)
+    coords, data = (tab.easting.values, tab.northing.values), tab.scalars.values
+    spacing = 250.0
+    chain = vb.Chain([("mean", vb.BlockReduce(np.mean, spacing=spacing)), ("spline", vb.Spline(damping=1e-6))])
+    chain.fit(coords, data)
+    grid = chain.grid(spacing=100.0)
+    masked = vb.distance_mask(coords, maxdist=150.0, grid=grid)
+    # the same pipeline through the oracles
+    _, labels = bo.block_split(coords, spacing=spacing)
+    _, be = bo.group_reduce(labels, coords[0], np.mean)
+    _, bn = bo.group_reduce(labels, coords[1], np.mean)
+    _, bd = bo.group_reduce(labels, data, np.mean)
+    force = vo.spline_fit(be, bn, bd, damping=1e-6)
+    ge, gn = vb.grid_coordinates(chain.region_, spacing=100.0)
+    ref = vo.predict(ge.ravel(), gn.ravel(), be, bn, 0.0, force).reshape(ge.shape)
+    inside = bo.distance_mask(coords, 150.0, (ge, gn))
+    got = np.asarray(masked["scalars"])
+    np.testing.assert_array_equal(np.isnan(got), ~inside)
+    assert np.max(np.abs(got[inside] - ref[inside])) <= 1e-6 * np.ptp(data)
+    np.testing.assert_allclose(chain.named_steps["spline"].force_coords_[0], be, rtol=1e-13)

@@ -143,3 +143,18 @@ def test_wide_predict_kernel_is_bit_identical(env, mindist):
     finally:
         lib.vb200_set_option(b"predict_wide", 0.0)
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+def test_batched_sweep_in_groups_when_memory_is_short(env):
+    "sweep_group caps how many damped systems are factored side by side (what a nearly full HBM does)"
+    vb, kernels, lib = env
+    e, nn, d = sample(900, seed=13)
+    dampings = [1e-5, 1e-4, 1e-3, 1e-2, 1e-1]
+    system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, None, e, nn, 0.0)
+    whole = system.solve_multi(e.size, dampings)
+    try:
+        assert lib.vb200_set_option(b"sweep_group", 2.0) == 0
+        grouped = system.solve_multi(e.size, dampings)  # batches of 2, 2, 1
+    finally:
+        lib.vb200_set_option(b"sweep_group", 0.0)
+    np.testing.assert_array_equal(grouped, whole)

@@ -46,6 +46,7 @@ struct Options {
     int chol_panel_tiles = 8;
     int gram_slab_chunks = 16;
     int gram_fused = 0;
+    int sweep_group = 0;  // damped systems factored side by side in vb200_gram_solve_multi (0 = as many as fit)
 } g_opt;
 
 // ---- cached workspace (grow-only, per process; one process per GPU) --------------------
@@ -319,6 +320,7 @@ int vb200_set_option(const char *key, double value)
     else if (k == "gram_slab_chunks") g_opt.gram_slab_chunks = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "solve_variant") vb_solve_variant = (int)value;
     else if (k == "gram_fused") g_opt.gram_fused = value != 0.0;
+    else if (k == "sweep_group") g_opt.sweep_group = value < 0 ? 0 : (int)value;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
     else if (k == "predict_minb") vb_predict_minb = (int)value;
@@ -700,6 +702,7 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
     long long group = (long long)((free_b > (1ull << 30) ? free_b - (1ull << 30) : 0) / (sizeof(double) * (size_t)stride));
     if (group > n_dampings) group = n_dampings;
     if (group > 64) group = 64;
+    if (g_opt.sweep_group > 0 && group > g_opt.sweep_group) group = g_opt.sweep_group;
     if (group < 1) return fail(VB200_E_NOMEM, "not enough device memory for one %lld x %lld factor", (long long)cols, (long long)cols);
     double *Lb, *inv_scale, *rhs, *xb, *damp_dev, *mm;
     int *d_info, *d_flags;
