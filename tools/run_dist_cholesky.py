@@ -52,10 +52,21 @@ for n in sizes:
         res["replicated_factor_ms"] = system.info.factor_ms
         system.info = vb._cabi.FitInfo()
         system.gram.copy_(keep)
-        res["distributed_s"], f_dist = timed(lambda: system.solve_distributed(n, damping))
-        res["distributed_factor_ms"] = system.info.factor_ms
-        res["distributed_solve_ms"] = system.info.solve_ms
-        system.info = vb._cabi.FitInfo()
+        for exchange in ("broadcast", "allreduce"):
+            vb.dist.set_panel_exchange(exchange)
+            system.gram.copy_(keep)
+            phases = {}
+            res[exchange + "_s"], f_x = timed(lambda: system.solve_distributed(n, damping, phase_times=phases))
+            # this rank's device time per phase: "broadcast" includes waiting for the owner's panel
+            res[exchange + "_rank0_phase_ms"] = {k: round(v, 2) for k, v in phases.items()}
+            res[exchange + "_factor_ms"] = system.info.factor_ms
+            system.info = vb._cabi.FitInfo()
+            if exchange == "broadcast":
+                f_dist = f_x
+            else:
+                res["allreduce_exchange_bit_identical"] = bool(np.array_equal(f_x, f_dist))
+        vb.dist.set_panel_exchange("broadcast")
+        res["distributed_s"], res["distributed_factor_ms"] = res["broadcast_s"], res["broadcast_factor_ms"]
     # every rank must hold the same answer
     mine = torch.from_numpy(f_dist).cuda()
     lo, hi = mine.clone(), mine.clone()

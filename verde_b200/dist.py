@@ -109,12 +109,34 @@ def use_distributed_cholesky(block_rows, panel_tiles, size=None):
     return len(panel_cyclic_schedule(block_rows, panel_tiles, size)) >= 2 * size
 
 
+_PANEL_EXCHANGE = "broadcast"
+
+
+def set_panel_exchange(mode):
+    """
+    How a factored Cholesky panel reaches the other ranks: ``"broadcast"`` (``ncclBroadcast``, a ring) or
+    ``"allreduce"`` (every other rank zeroes its copy of the panel and the ranks all-reduce it: x + 0 = x
+    exactly, and NCCL's all-reduce runs the NVLink-switch reduction (NVLS) and all channels, which its
+    broadcast does not).
+    """
+    global _PANEL_EXCHANGE
+    if mode not in ("broadcast", "allreduce"):
+        raise ValueError("panel exchange must be 'broadcast' or 'allreduce'")
+    _PANEL_EXCHANGE = mode
+
+
 def broadcast_(tensor, src):
     "In-place broadcast of a torch tensor from rank *src* (NCCL for CUDA tensors, gloo for CPU)."
     import torch.distributed as td
 
-    if world()[1] > 1:
-        td.broadcast(tensor, src=src)
+    rank, size = world()
+    if size > 1:
+        if _PANEL_EXCHANGE == "allreduce":
+            if rank != src:
+                tensor.zero_()
+            td.all_reduce(tensor, op=td.ReduceOp.SUM)
+        else:
+            td.broadcast(tensor, src=src)
     return tensor
 
 

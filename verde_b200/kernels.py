@@ -245,7 +245,7 @@ class GramSystem:
         _cabi.check(rc, "gram_solve_multi")
         return params
 
-    def solve_distributed(self, total_rows, damping, panel_tiles=8, out=None):
+    def solve_distributed(self, total_rows, damping, panel_tiles=8, out=None, phase_times=None):
         """
         Like ``solve`` on N > 1 ranks that all hold the all-reduced Gram matrix, but the m^3/3
         flops of the Cholesky are shared: outer panel p is factored by rank ``p % N`` and broadcast
@@ -265,19 +265,34 @@ class GramSystem:
         _cabi.check(lib.vb200_chol_begin(gram_ptr, _cabi.ptr(self.stats), cols, int(total_rows), float(damping)),
                     "chol_begin")
         offset, count = ctypes.c_int64(), ctypes.c_int64()
+        marks = []  # (phase, event) pairs on the library stream when the caller asked for a breakdown
+
+        def mark(phase):
+            if phase_times is not None:
+                event = self._torch.cuda.Event(enable_timing=True)
+                event.record()
+                marks.append((phase, event))
+
+        mark("start")
         for p, (k0, width, owner) in enumerate(schedule):
             if rank == owner:
                 _cabi.check(lib.vb200_chol_panel(gram_ptr, cols, k0, width), "chol_panel")
+            mark("panel")
             _cabi.check(lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count)),
                         "chol_panel_range")
             dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
+            mark("broadcast")
             for q0, qwidth, qowner in schedule[p + 1:]:
                 if qowner == rank:
                     _cabi.check(lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth), "chol_update")
+            mark("update")
         params = np.empty(cols, dtype=np.float64) if out is None else out  # host array or CUDA tensor
         rc = lib.vb200_chol_finish(gram_ptr, cols, _cabi.ptr(params), ctypes.byref(self.info))
         _remember(self.info)
         # a non-positive pivot is only recorded on the rank that owns its panel: agree before raising
+        if phase_times is not None:  # device time between consecutive marks, summed per phase (ms)
+            for (_, before), (phase, after) in zip(marks, marks[1:]):
+                phase_times[phase] = phase_times.get(phase, 0.0) + before.elapsed_time(after)
         lowest, highest = dist.agree_on_status(rc)
         _cabi.check(rc if rc != 0 else (lowest if lowest < 0 else highest), "chol_finish")
         return params
