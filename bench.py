@@ -213,9 +213,13 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(world, n_rank=50_000, m=50_000, grid=2000):
     base = "BASELINE configs[1]" if (n_rank, m, grid) == (50_000, 50_000, 2000) else "REDUCED-SIZE variant of configs[1]"
+    if world == 1 and m != n_rank:
+        base = ("BASELINE configs[2] on one GPU" if (n_rank, m, grid) == (400_000, 50_000, 10_000)
+                else "configs[2]-style system (separate forces)")
     return {
         "workload": ("{}: Spline(damping=1e-6, mindist=1e-5), CheckerBoard scatter of {} points, "
-                     "forces at data, grid {}x{}".format(base, n_rank, grid, grid) if world == 1 else
+                     "{}, grid {}x{}".format(base, n_rank, "forces at data" if m == n_rank else "{} separate forces".format(m),
+                                             grid, grid) if world == 1 else
                      "weak-scaled {} (= configs[2] at N=8 and full size): {} data rows sharded over {} ranks, {} forces, "
                      "grid {}x{} sharded".format(base, n_rank * world, world, m, grid, grid * world)),
         "n_data": n_rank * world, "n_forces": m, "grid_points": grid * grid * world,
@@ -235,6 +239,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=50_000, help="data points per rank (default: the BASELINE 50k)")
     ap.add_argument("--grid", type=int, default=2000, help="grid is GRID x GRID per rank")
+    ap.add_argument("--forces", type=int, default=None,
+                    help="number of forces (default: forces at the data on one GPU, 50000 separate forces on several); "
+                         "--gpus 1 --size 400000 --forces 50000 --grid 10000 is BASELINE configs[2] on ONE GPU")
     ap.add_argument("--cpu-sample", type=int, default=14000, help="n=m of the CPU baseline sample")
     ap.add_argument("--cholesky", default="auto", choices=["auto", "replicated", "distributed"],
                     help="N > 1: replicated m x m Cholesky on every rank, or panel-cyclic over the ranks")
@@ -271,11 +278,13 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n_rank, m = args.size, args.size if world == 1 else min(50_000, args.size)
+    n_rank = args.size
+    m = args.forces if args.forces else (args.size if world == 1 else min(50_000, args.size))
     n_total = n_rank * world
+    forces_at_data = world == 1 and m == n_total and not args.forces
     grid_shape = (args.grid, args.grid * world)
     npts_total = grid_shape[0] * grid_shape[1]
-    east, north, data, fe, fn, ge, gn = make_workload(n_total, m, grid_shape, forces_at_data=(world == 1))
+    east, north, data, fe, fn, ge, gn = make_workload(n_total, m, grid_shape, forces_at_data=forces_at_data)
     gx, gy = np.meshgrid(ge, gn)
     gx, gy = gx.ravel(), gy.ravel()
     a, b = vb.dist.shard_bounds(n_total, rank, world)
@@ -381,7 +390,7 @@ def main():
 
         h_e, h_n, h_d = pinned(east), pinned(north), pinned(data)
         h_gx, h_gy = pinned(gx), pinned(gy)
-        force_coords = None if world == 1 else (pinned(fe), pinned(fn))
+        force_coords = None if forces_at_data else (pinned(fe), pinned(fn))
         result = {}
 
         def api_step():
@@ -396,7 +405,7 @@ def main():
             api_step()
         e2e_steps = max(1, min(args.steps, 2))
         e2e_ms = timed(api_step, e2e_steps) / e2e_steps
-        h2d = 8 * ((b - a) * 3 + (0 if world == 1 else 2 * m) + 2 * m + 2 * (pb - pa) + m)
+        h2d = 8 * ((b - a) * 3 + (0 if forces_at_data else 2 * m) + 2 * m + 2 * (pb - pa) + m)
         d2h = 8 * (m + (pb - pa))
         e2e = {"value": npts_total / (e2e_ms * 1e-3) * 1e-6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
