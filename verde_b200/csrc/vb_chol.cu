@@ -24,59 +24,91 @@ namespace {
 constexpr int POTRF_THREADS = 128;
 constexpr int POTRF_BLK = 16;
 
-// Factor one diagonal tile in place (lower triangle).  Thread r owns row r; the tile
-// lives in shared memory (column-major, so a thread's accesses s[c*128 + r] are
-// conflict-free and L(c0.., k) rows are contiguous for LDS.128 broadcasts).  Left-looking
-// over 16-column blocks held in registers: the block is first updated with all columns to
-// its left (16 independent FMAs per own-row load), then factored column by column with
-// one shared-memory publish + barrier per pivot and per column.
+// Factor one diagonal tile in place (lower triangle).  Thread r owns row r; the tile lives in shared
+// memory (column-major, so a thread's accesses s[c*128 + r] are conflict-free and L(c0.., k) rows are
+// contiguous for LDS.128 broadcasts).  Left-looking over 16-column blocks held in registers:
+//   1. the block is updated with all columns to its left (16 independent FMAs per own-row load);
+//   2. the 16 x 16 diagonal block is factored by the ONE warp whose lanes own those rows, exchanging
+//      pivots and multipliers with shuffles -- no CTA barrier inside the 16 pivot steps;
+//   3. every row below solves its 16 entries against that block (forward substitution, independent per row).
+// Two CTA barriers per block instead of two per column (32 per block): the kernel is pure latency, and this
+// took it from 65 us to the time of the dependent chains themselves.  The operation order per element is the
+// one a column-by-column elimination performs, so the factor is bit-identical to the previous kernel's.
 __global__ void __launch_bounds__(POTRF_THREADS)
 vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info, long long stride)
 {
     extern __shared__ __align__(16) double s[];  // s[c * 128 + r]
-    __shared__ double s_piv[POTRF_BLK];
     const int r = threadIdx.x;
+    const int lane = r & 31;
     tile += (long long)blockIdx.x * stride;  // one CTA per matrix of a batch
     d_info += blockIdx.x;
+    // 128 KB through one 128-thread CTA: keep 16 independent 16-byte loads in flight per thread, or the
+    // staging (64 dependent round trips to L2) costs more than the factorisation
+#pragma unroll 16
     for (int idx = r; idx < VB_TILE_ELEMS / 2; idx += POTRF_THREADS)
-        reinterpret_cast<double2 *>(s)[idx] = reinterpret_cast<const double2 *>(tile)[idx];
+        reinterpret_cast<double2 *>(s)[idx] = __ldcg(reinterpret_cast<const double2 *>(tile) + idx);
     __syncthreads();
     for (int c0 = 0; c0 < VB_TILE; c0 += POTRF_BLK) {
         double a[POTRF_BLK];
 #pragma unroll
         for (int c = 0; c < POTRF_BLK; ++c) a[c] = s[(c0 + c) * VB_TILE + r];
-        for (int kp = 0; kp < c0; ++kp) {
-            const double lrk = s[kp * VB_TILE + r];
-            const double2 *lc = reinterpret_cast<const double2 *>(s + kp * VB_TILE + c0);
+        if (r >= c0) {  // rows above the block only hold the (ignored) upper triangle
+            for (int kp = 0; kp < c0; ++kp) {
+                const double lrk = s[kp * VB_TILE + r];
+                const double2 *lc = reinterpret_cast<const double2 *>(s + kp * VB_TILE + c0);
 #pragma unroll
-            for (int c2 = 0; c2 < POTRF_BLK / 2; ++c2) {
-                const double2 l = lc[c2];
-                a[2 * c2] = fma(-lrk, l.x, a[2 * c2]);
-                a[2 * c2 + 1] = fma(-lrk, l.y, a[2 * c2 + 1]);
+                for (int c2 = 0; c2 < POTRF_BLK / 2; ++c2) {
+                    const double2 l = lc[c2];
+                    a[2 * c2] = fma(-lrk, l.x, a[2 * c2]);
+                    a[2 * c2 + 1] = fma(-lrk, l.y, a[2 * c2 + 1]);
+                }
             }
         }
+        if ((r >> 5) == (c0 >> 5)) {
+            // the warp that owns rows c0 .. c0+15 (lanes lo .. lo+15) factors the diagonal block
+            const int lo = c0 & 31;
 #pragma unroll
-        for (int kk = 0; kk < POTRF_BLK; ++kk) {
-            const int cg = c0 + kk;
-            if (r == cg) {
-                const double piv = a[kk];
-                if (!(piv > 0.0)) atomicCAS(d_info, 0, k * VB_TILE + cg + 1);
-                s_piv[kk] = sqrt(piv);
+            for (int kk = 0; kk < POTRF_BLK; ++kk) {
+                const double piv = __shfl_sync(0xffffffffu, a[kk], lo + kk);
+                if (lane == lo + kk && !(piv > 0.0)) atomicCAS(d_info, 0, k * VB_TILE + c0 + kk + 1);
+                const double l = sqrt(piv);
+                const double x = (lane == lo + kk) ? l : a[kk] / l;
+                a[kk] = x;
+#pragma unroll
+                for (int c = kk + 1; c < POTRF_BLK; ++c) {
+                    const double lck = __shfl_sync(0xffffffffu, x, lo + c);  // L(c0+c, c0+kk)
+                    a[c] = fma(-x, lck, a[c]);
+                }
             }
-            __syncthreads();
-            const double l = s_piv[kk];
-            const double x = (r == cg) ? l : a[kk] / l;
-            a[kk] = x;
-            s[cg * VB_TILE + r] = x;
-            __syncthreads();
+            // lanes of this warp BELOW the block ran the same recurrence on their own rows: that is exactly
+            // their forward substitution, so they are finished too (lanes above the block hold don't-cares)
+            if (r >= c0) {
 #pragma unroll
-            for (int c = kk + 1; c < POTRF_BLK; ++c) a[c] = fma(-x, s[cg * VB_TILE + c0 + c], a[c]);
+                for (int c = 0; c < POTRF_BLK; ++c) s[(c0 + c) * VB_TILE + r] = a[c];
+            }
         }
+        __syncthreads();
+        if (r >= c0 + POTRF_BLK && (r >> 5) != (c0 >> 5)) {
+#pragma unroll
+            for (int kk = 0; kk < POTRF_BLK; ++kk) {
+                const double *lcol = s + (c0 + kk) * VB_TILE + c0;  // column c0+kk of the factored block
+                const double x = a[kk] / lcol[kk];
+                a[kk] = x;
+#pragma unroll
+                for (int c = kk + 1; c < POTRF_BLK; ++c) a[c] = fma(-x, lcol[c], a[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < POTRF_BLK; ++c) s[(c0 + c) * VB_TILE + r] = a[c];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int idx = r; idx < VB_TILE_ELEMS; idx += POTRF_THREADS) {
-        const int c = idx >> 7, rr = idx & 127;
-        tile[idx] = (rr >= c) ? s[idx] : 0.0;
+#pragma unroll 8
+    for (int idx = r; idx < VB_TILE_ELEMS / 2; idx += POTRF_THREADS) {
+        const int c = idx >> 6, rr = (idx & 63) * 2;
+        double2 v = reinterpret_cast<const double2 *>(s)[idx];
+        if (rr < c) v.x = 0.0;
+        if (rr + 1 < c) v.y = 0.0;
+        reinterpret_cast<double2 *>(tile)[idx] = v;
     }
 }
 
@@ -85,23 +117,32 @@ vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info,
 // memory; row blocks of 32 unknowns live in registers:
 //   a[c] -= x_prev * L[c][prev]   (prev columns: x re-read from the tile itself)
 //   in-block forward substitution, fully unrolled.
-constexpr int TRSM_THREADS = 128;
+// 128^3/2 FMAs per tile is 8 us of one SM's FP64 pipe, and L_kk takes 128 KB of shared memory, so only one
+// CTA fits per SM: with one tile per CTA the ~390 tiles of an early block column ran as three waves of
+// one-warp-per-scheduler CTAs.  A CTA now solves up to TRSM_MAX_TILES tiles against the same staged L_kk
+// (128 threads per tile); the launcher picks ceil(tiles / SMs) so that a block column is ONE wave with the
+// tiles of an SM running concurrently, and small problems keep one tile per CTA.
+constexpr int TRSM_MAX_TILES = 4;
 constexpr int TRSM_BLK = 32;
 
-__global__ void __launch_bounds__(TRSM_THREADS)
+__global__ void __launch_bounds__(128 * TRSM_MAX_TILES)
 vb_trsm_tiles_kernel(double *__restrict__ Lmat, int T, int k, long long stride)
 {
     extern __shared__ __align__(16) double sL[];  // sL[c * 128 + r] = L_kk(r, c)
     __shared__ double s_inv[VB_TILE];
     Lmat += (long long)blockIdx.y * stride;  // grid.y = matrix of a batch
     const double *diag = Lmat + vb_tile_index(k, k, T) * VB_TILE_ELEMS;
-    double *tile = Lmat + vb_tile_index(k + 1 + blockIdx.x, k, T) * VB_TILE_ELEMS;
-    const int r = threadIdx.x;
-    for (int idx = threadIdx.x; idx < VB_TILE_ELEMS / 2; idx += TRSM_THREADS)
-        reinterpret_cast<double2 *>(sL)[idx] = reinterpret_cast<const double2 *>(diag)[idx];
+    const int r = threadIdx.x & (VB_TILE - 1);
+    const int tiles_per_cta = blockDim.x >> 7;
+    const int below = blockIdx.x * tiles_per_cta + (threadIdx.x >> 7);  // which tile under the diagonal
+#pragma unroll 8
+    for (int idx = threadIdx.x; idx < VB_TILE_ELEMS / 2; idx += blockDim.x)
+        reinterpret_cast<double2 *>(sL)[idx] = __ldcg(reinterpret_cast<const double2 *>(diag) + idx);
     __syncthreads();
-    s_inv[r] = 1.0 / sL[r * VB_TILE + r];
+    if (threadIdx.x < VB_TILE) s_inv[r] = 1.0 / sL[r * VB_TILE + r];
     __syncthreads();
+    if (below >= T - k - 1) return;  // ragged last CTA (no barrier follows)
+    double *tile = Lmat + vb_tile_index(k + 1 + below, k, T) * VB_TILE_ELEMS;
 
     for (int cb = 0; cb < VB_TILE / TRSM_BLK; ++cb) {
         double a[TRSM_BLK];
@@ -365,13 +406,22 @@ cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, 
     int potrf_smem, trsm_smem;
     if ((err = chol_set_attributes(&potrf_smem, &trsm_smem)) != cudaSuccess) return err;
     if (batch < 1) batch = 1;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+    }
     for (int kk = 0; kk < pw; ++kk) {
         const int k = k0 + kk;
         vb_potrf_tile_kernel<<<batch, POTRF_THREADS, potrf_smem, stream>>>(
             L + vb_tile_index(k, k, T) * VB_TILE_ELEMS, k, d_info, stride);
         ++vb_launch_counter;
         if (k + 1 < T) {
-            vb_trsm_tiles_kernel<<<dim3(T - k - 1, batch), TRSM_THREADS, trsm_smem, stream>>>(L, T, k, stride);
+            const int ntiles = T - k - 1;
+            int tpc = (int)(((long long)ntiles * batch + sms - 1) / sms);
+            tpc = tpc < 1 ? 1 : (tpc > TRSM_MAX_TILES ? TRSM_MAX_TILES : tpc);
+            vb_trsm_tiles_kernel<<<dim3((ntiles + tpc - 1) / tpc, batch), 128 * tpc, trsm_smem, stream>>>(L, T, k, stride);
             ++vb_launch_counter;
         }
         if (kk + 1 < pw) {
