@@ -3,7 +3,6 @@ GPU tests at sizes the CPU oracle cannot reach in seconds, through size-independ
 properties (linearity, row-shard additivity, backward error of the solve, agreement of
 SplineCV's Gram-reuse sweep with plain cross_val_score) -- all through the C ABI.
 """
-import ctypes
 import warnings
 
 import numpy as np

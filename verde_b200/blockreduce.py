@@ -24,7 +24,7 @@ import numpy as np
 from sklearn.base import BaseEstimator
 
 from . import _cabi
-from .base import check_coordinates, check_fit_input, n_1d_arrays
+from .base import check_coordinates, check_fit_input
 from .coords import get_region, grid_coordinates
 
 MEAN, SUM, MIN, MAX, COUNT, MEDIAN, VAR, WMEAN, WVAR, INV_SUM_W = range(10)

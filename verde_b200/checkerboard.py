@@ -4,7 +4,6 @@
 generator for fixtures and benchmarks, not as a kernel target.
 """
 import numpy as np
-import pandas as pd
 
 from .base import BaseGridder, check_data, get_instance_region, project_coordinates
 from .coords import check_region, scatter_points
