@@ -90,6 +90,13 @@ int vb200_jacobian_2d(const double *east, const double *north, int64_t n,
 int vb200_predict(const double *east, const double *north, int64_t n, const double *force_east,
                   const double *force_north, const double *forces, int64_t m, double mindist,
                   double *result);
+/* several coefficient vectors on the SAME forces (a verde.Vector of Splines on shared coordinates,
+ * verde/vector.py:134-141: `tuple(comp.predict(coordinates) for comp in self.components)` evaluates
+ * every Green's function once per component; here once per pair).  forces: n_components x m,
+ * result: n_components x n, both row-major; each row equals its own vb200_predict bit for bit. */
+int vb200_predict_multi(const double *east, const double *north, int64_t n, const double *force_east,
+                        const double *force_north, const double *forces, int64_t m,
+                        int32_t n_components, double mindist, double *result);
 /* replaces verde/vector.py:443-458 predict_2d_numba(..., mindist, poisson, forces, vec_east,
  * vec_north); forces has length 2m (east forces, then north forces). */
 int vb200_predict_2d(const double *east, const double *north, int64_t n,

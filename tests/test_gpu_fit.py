@@ -280,6 +280,28 @@ def test_vector_of_splines_shares_one_factorisation(vb, golden_spline):
     assert mixed.components[1].damping == 1e-2 and mixed.components[1].force_.shape == e.shape
 
 
+def test_vector_of_splines_predicts_all_components_in_one_pass(vb, golden_spline):
+    "Vector.predict of Splines on shared forces = vb200_predict_multi; equals component-wise predict bit for bit"
+    g = golden_spline
+    e, n, d = g["east"], g["north"], g["data"]
+    d2 = np.cos(e / 300.0) * 40.0 + n / 90.0
+    vec = vb.Vector([vb.Spline(damping=1e-4), vb.Spline(damping=1e-4)]).fit((e, n), (d, d2))
+    assert vec._splines_share_forces()
+    grid = (g["grid_east"], g["grid_north"])
+    together = vec.predict(grid)
+    for comp, got in zip(vec.components, together):
+        want = comp.predict(grid)
+        assert got.shape == want.shape and got.dtype == want.dtype
+        np.testing.assert_array_equal(got, want)
+    # different dampings still share forces (fit separately, predicted together); different force sets do not
+    mixed = vb.Vector([vb.Spline(damping=1e-4), vb.Spline(damping=1e-2)]).fit((e, n), (d, d2))
+    assert mixed._splines_share_forces()
+    np.testing.assert_array_equal(mixed.predict(grid)[1], mixed.components[1].predict(grid))
+    apart = vb.Vector([vb.Spline(damping=1e-4), vb.Spline(damping=1e-4, force_coords=(e[::2], n[::2]))]).fit((e, n), (d, d2))
+    assert not apart._splines_share_forces()
+    np.testing.assert_array_equal(apart.predict(grid)[1], apart.components[1].predict(grid))
+
+
 def test_chain_of_splines(vb, golden_spline):
     g = golden_spline
     e, n, d = g["east"], g["north"], g["data"]

@@ -178,3 +178,30 @@ def test_predict_2d_vs_oracle(kernels, oracle, golden_vector, exact):
     ne = ge.size
     assert np.all(np.abs(oe - g["grid_east_d1em3"].ravel()) <= tol[:ne])
     assert np.all(np.abs(on - g["grid_north_d1em3"].ravel()) <= tol[ne:])
+
+
+@pytest.mark.parametrize("ncomp,npts,m,mindist", [(2, 70_000, 3000, 0.0), (3, 70_000, 3000, 1e-5), (2, 33, 7, 0.0),
+                                                  (4, 5000, 40_000, 1e-5), (5, 999, 1200, 0.0)])
+def test_predict_multi_equals_one_predict_per_component(kernels, ncomp, npts, m, mindist):
+    """vb200_predict_multi: several coefficient vectors on shared forces, Green's function evaluated once per
+    pair; same lane striding / chunking / force split as vb200_predict -> every component bit-identical."""
+    rng = np.random.RandomState(ncomp * 1000 + m)
+    e, n = rng.uniform(0, 5000, npts), rng.uniform(-5000, 0, npts)
+    fe, fn = rng.uniform(0, 5000, m), rng.uniform(-5000, 0, m)
+    forces = rng.normal(size=(ncomp, m))
+    multi = kernels.predict_multi_b200(e, n, fe, fn, mindist, forces, np.empty((ncomp, npts)))
+    for k in range(ncomp):
+        single = kernels.predict_b200(e, n, fe, fn, mindist, forces[k], np.empty(npts))
+        np.testing.assert_array_equal(multi[k], single)
+
+
+def test_predict_multi_non_finite_inputs_stay_in_their_component(kernels):
+    rng = np.random.RandomState(3)
+    e, n = rng.uniform(0, 10, 300), rng.uniform(0, 10, 300)
+    fe, fn = rng.uniform(0, 10, 50), rng.uniform(0, 10, 50)
+    forces = rng.normal(size=(2, 50))
+    forces[1, 7] = np.nan
+    e[5] = np.inf
+    out = kernels.predict_multi_b200(e, n, fe, fn, 0.0, forces, np.empty((2, 300)))
+    assert np.isnan(out[1]).all()                         # a NaN coefficient poisons its own component ...
+    assert np.isnan(out[0, 5]) and np.isfinite(np.delete(out[0], 5)).all()  # ... and only that one

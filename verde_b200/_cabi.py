@@ -57,6 +57,7 @@ SIGNATURES = {
     "vb200_jacobian": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, ctypes.c_void_p]),
     "vb200_jacobian_2d": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, ctypes.c_void_p]),
     "vb200_predict": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 3 + [i64, dbl, ctypes.c_void_p]),
+    "vb200_predict_multi": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 3 + [i64, ctypes.c_int32, dbl, ctypes.c_void_p]),
     "vb200_predict_2d": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 3 + [i64, dbl, dbl] + [ctypes.c_void_p] * 2),
     "vb200_spline_fit": (ctypes.c_int, [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_spline_fit_2d": (ctypes.c_int, [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),

@@ -87,9 +87,33 @@ class Vector(BaseGridder):
                                        else tuple(i.copy() for i in force_coords))
             estimator.fit_info_ = dict(kernels.LAST_FIT_INFO)
 
+    def _splines_share_forces(self):
+        "Fitted Splines on the same force positions and mindist: one Green's evaluation serves every component."
+        comps = self.components
+        if len(comps) < 2 or dist.sharding_active() or any(type(c) is not Spline for c in comps):
+            return False
+        if any(not hasattr(c, "force_") or c.mindist != comps[0].mindist for c in comps):
+            return False
+        first = n_1d_arrays(comps[0].force_coords_, n=2)
+        return all(c.force_.size == comps[0].force_.size
+                   and all(np.array_equal(a, b) for a, b in zip(n_1d_arrays(c.force_coords_, n=2), first))
+                   for c in comps[1:])
+
     def predict(self, coordinates):
         check_is_fitted(self, ["region_"])
-        return tuple(comp.predict(coordinates) for comp in self.components)
+        if not self._splines_share_forces():
+            return tuple(comp.predict(coordinates) for comp in self.components)
+        # same contract as Spline.predict for each component (verde/spline.py:486-499), one pass over the pairs
+        shape = np.broadcast(*coordinates[:2]).shape
+        east, north = n_1d_arrays(coordinates, n=2)
+        if east.size != north.size:
+            east, north = (np.ravel(c) for c in np.broadcast_arrays(*coordinates[:2]))
+        force_east, force_north = n_1d_arrays(self.components[0].force_coords_, n=2)
+        forces = np.stack([np.asarray(c.force_, dtype=np.float64) for c in self.components])
+        out = np.empty((forces.shape[0], east.size), dtype=np.float64)
+        kernels.predict_multi_b200(east, north, force_east, force_north, self.components[0].mindist, forces, out)
+        dtype = east.dtype if np.issubdtype(east.dtype, np.floating) else np.float64
+        return tuple(out[k].astype(dtype, copy=False).reshape(shape) for k in range(forces.shape[0]))
 
 
 class Chain(BaseGridder):

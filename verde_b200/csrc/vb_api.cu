@@ -440,6 +440,45 @@ int vb200_predict(const double *east, const double *north, int64_t n, const doub
     return 0;
 }
 
+int vb200_predict_multi(const double *east, const double *north, int64_t n, const double *force_east,
+                        const double *force_north, const double *forces, int64_t m, int32_t n_components,
+                        double mindist, double *result)
+{
+    if (n < 0 || m < 0 || n_components < 1) return fail(VB200_E_BADARG, "bad sizes");
+    if (n == 0) return 0;
+    if (!east || !north || !result || (m > 0 && (!force_east || !force_north || !forces)))
+        return fail(VB200_E_BADARG, "null pointer");
+    if (m > 0x7fffffffLL) return fail(VB200_E_BADARG, "too many forces");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dfe, *dfn, *df;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("in_fe", force_east, m, &dfe, st));
+    CU(stage_in("in_fn", force_north, m, &dfn, st));
+    CU(stage_in("in_f_multi", forces, m * n_components, &df, st));
+    OutBuf ob;
+    CU(stage_out("out_pred_multi", result, n * n_components, &ob));
+    int pts, nsplit;
+    vb_predict_plan(n, m, &pts, &nsplit);
+    // components go through the kernel three (or two) at a time; a single leftover uses the plain kernel
+    for (int q0 = 0; q0 < n_components;) {
+        const int left = n_components - q0;
+        const int k = left >= 3 && left != 4 ? 3 : (left >= 2 ? 2 : 1);
+        double *scratch = nullptr;
+        if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * (size_t)k * nsplit * n, (void **)&scratch));
+        if (k == 1)
+            CU(vb_launch_predict(de, dn, n, dfe, dfn, df + (long long)q0 * m, m, mindist, g_opt.predict_exact, pts, nsplit,
+                                 scratch, ob.dev + (long long)q0 * n, st));
+        else
+            CU(vb_launch_predict_multi(de, dn, n, dfe, dfn, df + (long long)q0 * m, m, k, mindist, g_opt.predict_exact, nsplit,
+                                       scratch, ob.dev + (long long)q0 * n, st));
+        q0 += k;
+    }
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int vb200_predict_2d(const double *east, const double *north, int64_t n,
                      const double *force_east, const double *force_north, const double *forces,
                      int64_t m, double mindist, double poisson, double *vec_east,

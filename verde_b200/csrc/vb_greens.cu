@@ -227,6 +227,101 @@ vb_predict2d_kernel(const double *__restrict__ east, const double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// K3 for several coefficient vectors on ONE set of force coordinates: a Vector of Splines on shared
+// coordinates (verde/vector.py:114-141 predicts component by component, i.e. re-evaluates every Green's
+// function per component).  The Green's function is evaluated once per pair and fed to NRHS accumulators:
+// 21 + NRHS FP64 slots per pair instead of NRHS * 22.  Same lane striding and chunking as
+// vb_predict_kernel, so every component is bit-identical to its own single predict.
+// ---------------------------------------------------------------------------
+constexpr int PREDM_PTS = 4;
+
+template <int MODE, int NRHS>
+__global__ void __launch_bounds__(PRED_THREADS, 2)
+vb_predict_multi_kernel(const double *__restrict__ east, const double *__restrict__ north, long long npts,
+                        const double *__restrict__ fe, const double *__restrict__ fn,
+                        const double *__restrict__ force /* [NRHS][m_total] */, int m_begin_stride, int m_total,
+                        double mindist, double *__restrict__ out /* [NRHS][gridDim.y][npts] */)
+{
+    constexpr int PTS = PREDM_PTS, REP = PRED_TAB_REP;
+    extern __shared__ __align__(16) double s_tab[];
+    __shared__ double s_fe[PRED_CHUNK], s_fn[PRED_CHUNK], s_f[NRHS][PRED_CHUNK];
+    __shared__ double s_out[NRHS][PRED_WARPS * PTS];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MODE != 2) vb_logtab_stage<REP>(s_tab, vb_logtab_global);
+    const double2 *tab = reinterpret_cast<const double2 *>(s_tab) + (lane & (REP - 1));
+    const int m0 = min(m_total, (int)blockIdx.y * m_begin_stride);
+    const int m1 = min(m_total, m0 + m_begin_stride);
+    const long long p0 = ((long long)blockIdx.x * PRED_WARPS + warp) * PTS;
+    double px[PTS], py[PTS], acc[PTS][NRHS];
+#pragma unroll
+    for (int p = 0; p < PTS; ++p) {
+        const long long idx = min(p0 + p, npts - 1);
+        px[p] = east[idx];
+        py[p] = north[idx];
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) acc[p][q] = 0.0;
+    }
+    int poisoned = 0;
+    for (int c0 = m0; c0 < m1; c0 += PRED_CHUNK) {
+        const int cn = min(PRED_CHUNK, m1 - c0);
+        __syncthreads();
+        int bad = 0;
+        for (int t = threadIdx.x; t < cn; t += PRED_THREADS) {
+            const double a = fe[c0 + t], b = fn[c0 + t];
+            s_fe[t] = a;
+            s_fn[t] = b;
+            if (!(isfinite(a) && isfinite(b))) bad |= 128;  // non-finite force coordinates poison every component
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) {
+                const double c = force[(long long)q * m_total + c0 + t];
+                s_f[q][t] = c;
+                if (!isfinite(c)) bad |= 1 << q;          // a non-finite coefficient only its own component
+            }
+        }
+        // __syncthreads_or only says "some thread saw one": one vote per flag
+        if (__syncthreads_or(bad & 128)) poisoned |= 128;
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q)
+            if (__syncthreads_or(bad & (1 << q))) poisoned |= 1 << q;
+#pragma unroll 2
+        for (int j = lane; j < cn; j += 32) {
+            const double fx = s_fe[j], fy = s_fn[j];
+            double fc[NRHS];
+#pragma unroll
+            for (int q = 0; q < NRHS; ++q) fc[q] = s_f[q][j];
+#pragma unroll
+            for (int p = 0; p < PTS; ++p) {
+                double g;
+                if (MODE == 0) g = vb_greens_fast<false, REP>(px[p] - fx, py[p] - fy, mindist, tab);
+                else if (MODE == 1) g = vb_greens_fast<true, REP>(px[p] - fx, py[p] - fy, mindist, tab);
+                else g = vb_greens_exact(px[p] - fx, py[p] - fy, mindist);
+#pragma unroll
+                for (int q = 0; q < NRHS; ++q) acc[p][q] = fma(g, fc[q], acc[p][q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PTS; ++p) {
+        const bool bad_point = !(isfinite(px[p]) && isfinite(py[p]));
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) {
+            double v = acc[p][q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (MODE != 2 && (bad_point || (poisoned & (128 | (1 << q))))) v = __longlong_as_double(0x7ff8000000000000LL);
+            if (lane == 0) s_out[q][warp * PTS + p] = v;
+        }
+    }
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * PRED_WARPS * PTS;
+    for (int t = threadIdx.x; t < NRHS * PRED_WARPS * PTS; t += PRED_THREADS) {
+        const int q = t / (PRED_WARPS * PTS), i = t % (PRED_WARPS * PTS);
+        if (base + i < npts) out[((long long)q * gridDim.y + blockIdx.y) * npts + base + i] = s_out[q][i];
+    }
+}
+
 // sum the force-split partials in fixed order: out[i] = sum_s part[s][i]
 __global__ void vb_reduce_splits_kernel(const double *__restrict__ part, long long npts, int nsplit,
                                         double *__restrict__ out)
@@ -436,6 +531,56 @@ cudaError_t vb_launch_predict2d(const double *e, const double *n, long long npts
         const unsigned nb = (unsigned)((npts + 255) / 256);
         vb_reduce_splits_kernel<<<nb, 256, 0, stream>>>(de, npts, nsplit, out_e);
         vb_reduce_splits_kernel<<<nb, 256, 0, stream>>>(dn, npts, nsplit, out_n);
+        err = cudaGetLastError();
+    }
+    return err;
+}
+
+template <int NRHS>
+static cudaError_t launch_predict_multi(int mode, dim3 grid, const double *e, const double *n, long long npts,
+                                        const double *fe, const double *fn, const double *f, int stride, int m,
+                                        double mindist, double *dst, cudaStream_t stream)
+{
+    cudaError_t err;
+    if (mode == 0) {
+        err = cudaFuncSetAttribute(vb_predict_multi_kernel<0, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_TAB_BYTES);
+        if (err != cudaSuccess) return err;
+        vb_predict_multi_kernel<0, NRHS><<<grid, PRED_THREADS, PRED_TAB_BYTES, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, dst);
+    } else if (mode == 1) {
+        err = cudaFuncSetAttribute(vb_predict_multi_kernel<1, NRHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_TAB_BYTES);
+        if (err != cudaSuccess) return err;
+        vb_predict_multi_kernel<1, NRHS><<<grid, PRED_THREADS, PRED_TAB_BYTES, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, dst);
+    } else {
+        vb_predict_multi_kernel<2, NRHS><<<grid, PRED_THREADS, 16, stream>>>(e, n, npts, fe, fn, f, stride, m, mindist, dst);
+    }
+    return cudaGetLastError();
+}
+
+// f: [nrhs][m] coefficient vectors on the same forces; out: [nrhs][npts]; nrhs = 2 or 3.
+// scratch: nrhs*nsplit*npts doubles when nsplit > 1.
+cudaError_t vb_launch_predict_multi(const double *e, const double *n, long long npts, const double *fe,
+                                    const double *fn, const double *f, long long m, int nrhs, double mindist,
+                                    int exact, int nsplit, double *scratch, double *out, cudaStream_t stream)
+{
+    if (npts == 0) return cudaSuccess;
+    if (m == 0) return cudaMemsetAsync(out, 0, sizeof(double) * npts * nrhs, stream);
+    if (nrhs != 2 && nrhs != 3) return cudaErrorInvalidValue;
+    cudaError_t err = vb_init_tables();
+    if (err != cudaSuccess) return err;
+    const int mode = (exact || !(mindist >= 0.0)) ? 2 : (mindist != 0.0 ? 1 : 0);
+    const int stride = (int)((m + nsplit - 1) / nsplit);
+    dim3 grid((unsigned)((npts + (long long)PRED_WARPS * PREDM_PTS - 1) / ((long long)PRED_WARPS * PREDM_PTS)), nsplit);
+    double *dst = nsplit > 1 ? scratch : out;
+    err = nrhs == 2 ? launch_predict_multi<2>(mode, grid, e, n, npts, fe, fn, f, stride, (int)m, mindist, dst, stream)
+                    : launch_predict_multi<3>(mode, grid, e, n, npts, fe, fn, f, stride, (int)m, mindist, dst, stream);
+    if (err != cudaSuccess) return err;
+    ++vb_launch_counter;
+    if (nsplit > 1) {
+        for (int q = 0; q < nrhs; ++q) {
+            vb_reduce_splits_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, stream>>>(scratch + (long long)q * nsplit * npts, npts,
+                                                                                   nsplit, out + (long long)q * npts);
+            ++vb_launch_counter;
+        }
         err = cudaGetLastError();
     }
     return err;

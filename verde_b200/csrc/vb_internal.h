@@ -52,6 +52,9 @@ cudaError_t vb_launch_predict(const double *e, const double *n, long long npts, 
                               const double *fn, const double *f, long long m, double mindist,
                               int exact, int pts, int nsplit, double *scratch, double *out,
                               cudaStream_t stream);
+cudaError_t vb_launch_predict_multi(const double *e, const double *n, long long npts, const double *fe,
+                                    const double *fn, const double *f, long long m, int nrhs, double mindist,
+                                    int exact, int nsplit, double *scratch, double *out, cudaStream_t stream);
 cudaError_t vb_launch_predict2d(const double *e, const double *n, long long npts, const double *fe,
                                 const double *fn, const double *f, long long m, double mindist,
                                 double poisson, int exact, int pts, int nsplit, double *scratch,

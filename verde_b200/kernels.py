@@ -9,6 +9,8 @@ here                         reference
 ===========================  ==================================================
 jacobian_b200                verde/spline.py:642-650  jacobian_numba
 predict_b200                 verde/spline.py:629-639  predict_numba
+predict_multi_b200           the same for several coefficient vectors on shared forces
+                             (verde/vector.py:134-141 Vector.predict)
 jacobian_2d_b200             verde/vector.py:461-475  jacobian_2d_numba
 predict_2d_b200              verde/vector.py:443-458  predict_2d_numba
 least_squares                verde/base/least_squares.py:17-71
@@ -59,6 +61,25 @@ def predict_b200(east, north, force_east, force_north, mindist, forces, result):
                                   _cabi.ptr(f), f.size, float(mindist), _cabi.ptr(out)), "predict")
     if not direct:
         result[:] = out
+    return result
+
+
+def predict_multi_b200(east, north, force_east, force_north, mindist, forces, result):
+    """
+    ``result[k]`` = predict with coefficient vector ``forces[k]`` on the shared forces, for all k at once
+    (one Green's evaluation per pair instead of one per component).  forces: (k, m); result: (k, n) float64.
+    """
+    lib = _cabi.require_device()
+    e, n, fe, fn = (_cabi.f64(a) for a in (east, north, force_east, force_north))
+    f = np.ascontiguousarray(forces, dtype=np.float64)
+    if f.ndim != 2 or f.shape[1] != fe.size:
+        raise ValueError("forces must have shape (components, n_forces)")
+    direct = result.dtype == np.float64 and result.flags.c_contiguous and result.shape == (f.shape[0], e.size)
+    out = result if direct else np.empty((f.shape[0], e.size), dtype=np.float64)
+    _cabi.check(lib.vb200_predict_multi(_cabi.ptr(e), _cabi.ptr(n), e.size, _cabi.ptr(fe), _cabi.ptr(fn), _cabi.ptr(f),
+                                        fe.size, f.shape[0], float(mindist), _cabi.ptr(out)), "predict_multi")
+    if not direct:
+        result[...] = out
     return result
 
 
