@@ -729,7 +729,8 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
     const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
     const long long Mpad = (long long)T * VB_TILE;
     const long long stride = vb200_gram_doubles(cols);
-    // how many factors fit side by side: leave the allocator 1 GB of slack
+    // how many factors fit side by side: at most 60 % of what is free (the workspace is cached, and the
+    // caller still needs room for its own tensors, panels and predict scratch afterwards)
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     {
@@ -738,7 +739,7 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
         auto it = g_ws.find(std::to_string(dev) + ":chol_batch");
         if (it != g_ws.end()) free_b += it->second.bytes;  // re-usable
     }
-    long long group = (long long)((free_b > (1ull << 30) ? free_b - (1ull << 30) : 0) / (sizeof(double) * (size_t)stride));
+    long long group = (long long)((size_t)(0.6 * (double)free_b) / (sizeof(double) * (size_t)stride));
     if (group > n_dampings) group = n_dampings;
     if (group > 64) group = 64;
     if (g_opt.sweep_group > 0 && group > g_opt.sweep_group) group = g_opt.sweep_group;
