@@ -311,3 +311,28 @@ def test_chain_of_splines(vb, golden_spline):
     np.testing.assert_allclose(chain.predict((e, n)), first.predict((e, n)) + second.predict((e, n)), rtol=0,
                                atol=1e-9 * np.ptp(d))
     assert set(chain.named_steps) == {"smooth", "detail"}
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 2), (3, 2), (127, 127), (128, 128), (129, 129), (257, 130), (130, 257),
+                                 (1000, 1), (385, 384)])
+def test_tiny_and_tile_boundary_systems_vs_oracle(vb, oracle, n, m):
+    """One point, one force, sizes either side of the 128-wide tiles, more forces than data: forces and
+    predictions against the CPU oracle (well-conditioned: damping 1e-2 on the scaled system)."""
+    rng = np.random.RandomState(1000 * n + m)
+    e, nn = rng.uniform(0, 100, n), rng.uniform(0, 100, n)
+    d = np.sin(e / 17.0) + np.cos(nn / 23.0) + 2.0
+    w = rng.uniform(0.5, 2.0, n)
+    if m == n:
+        force_coords, fe, fn = None, e, nn
+    else:
+        fe, fn = rng.uniform(0, 100, m), rng.uniform(0, 100, m)
+        force_coords = (fe, fn)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sp = vb.Spline(damping=1e-2, force_coords=force_coords).fit((e, nn), d, weights=w)
+    ref = oracle.spline_fit(e, nn, d, weights=w, damping=1e-2, force_east=fe, force_north=fn)
+    assert sp.force_.shape == (m,)
+    np.testing.assert_allclose(sp.force_, ref, rtol=0, atol=1e-8 * max(np.max(np.abs(ref)), 1e-300))
+    pe, pn = rng.uniform(0, 100, 50), rng.uniform(0, 100, 50)
+    np.testing.assert_allclose(sp.predict((pe, pn)), oracle.predict(pe, pn, fe, fn, 0.0, ref), rtol=0,
+                               atol=1e-8 * max(np.max(np.abs(d)), 1.0))
