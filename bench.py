@@ -429,10 +429,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(world, n_rank, m, args.grid),
-                       cholesky=("single GPU" if world == 1 else
-                                 "panel-cyclic over {} ranks, NCCL panel broadcast".format(world) if dist_chol else
-                                 "replicated on every rank")),
+        "config": workload_config(world, n_rank, m, args.grid),  # identical to the reference arm's config
+        "cholesky": ("single GPU" if world == 1 else
+                     "panel-cyclic over {} ranks, NCCL panel broadcast".format(world) if dist_chol else
+                     "replicated on every rank"),
         "fit_s": fit_s, "predict_s": pred_s, "predict_gpts_per_s": (pb - pa) * world / pred_s * 1e-9,
         "predict_gpairs_per_s": n_pairs / pred_s * 1e-9,
         "fit_phases_ms": {k: phase["info"][k] for k in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms")},
