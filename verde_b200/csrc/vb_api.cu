@@ -319,6 +319,7 @@ int vb200_set_option(const char *key, double value)
     else if (k == "chol_panel_tiles") g_opt.chol_panel_tiles = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "gram_slab_chunks") g_opt.gram_slab_chunks = value < 1 ? 1 : (value > VB_MAX_KCHUNKS ? VB_MAX_KCHUNKS : (int)value);
     else if (k == "solve_variant") vb_solve_variant = (int)value;
+    else if (k == "trsm_tiles") vb_trsm_tiles = (int)value;
     else if (k == "gram_fused") g_opt.gram_fused = value != 0.0;
     else if (k == "sweep_group") g_opt.sweep_group = value < 0 ? 0 : (int)value;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;

@@ -420,7 +420,10 @@ cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, 
         if (k + 1 < T) {
             const int ntiles = T - k - 1;
             int tpc = (int)(((long long)ntiles * batch + sms - 1) / sms);
-            tpc = tpc < 1 ? 1 : (tpc > TRSM_MAX_TILES ? TRSM_MAX_TILES : tpc);
+            // one wave when it fits in <= 3 tiles per SM (37 us at T = 391); beyond that several waves are
+            // inevitable and 2 tiles per CTA measured best (batched sweep: 11.6 ms per job vs 12.9 / 12.3 / 13.2)
+            tpc = tpc < 1 ? 1 : (tpc > 3 ? 2 : tpc);
+            if (vb_trsm_tiles >= 1 && vb_trsm_tiles <= TRSM_MAX_TILES) tpc = vb_trsm_tiles;
             vb_trsm_tiles_kernel<<<dim3((ntiles + tpc - 1) / tpc, batch), 128 * tpc, trsm_smem, stream>>>(L, T, k, stride);
             ++vb_launch_counter;
         }
@@ -485,6 +488,7 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
 }
 
 // x (length T*128) is overwritten by the solution of L L^T x = b.
+int vb_trsm_tiles = 0;    // tiles per trsm CTA: 0 = ceil(tiles / SMs) capped at 4
 int vb_solve_variant = 1;  // 1: one cooperative launch per sweep, 0: two launches per block row
 
 static cudaError_t solve_cooperative(const double *L, int T, double *x, int *flags, cudaStream_t stream, int batch,

@@ -129,7 +129,7 @@ cudaError_t vb_solve_tiled(const double *L, int T, double *x, int *flags, cudaSt
 cudaError_t vb_launch_scale_system_batched(const double *G, int T, long long cols, const double *inv_scale,
                                            const double *dampings_dev, int batch, double *L,
                                            long long stride, cudaStream_t stream);
-extern int vb_solve_variant;
+extern int vb_solve_variant, vb_trsm_tiles;
 
 // ---- block reductions and the distance mask (vb_block.cu) --------------------------------------
 // reduction codes of vb200_block_aggregate (mirrored in include/verde_b200.h)
