@@ -2,7 +2,7 @@
 Parity at the HEADLINE size (BASELINE config 2: 50 000 points, forces at the data, damping 1e-6,
 mindist 1e-5): the CPU oracle (bit-exact restatement of the reference, tests/test_oracle.py) is run on
 the GPU box's host cores (needs ~80 GB of RAM and ~10 min) and compared with the B200 path on the
-same inputs.  Prints one JSON object.   python tools/parity_full_config2.py [n]
+same inputs.  Prints one JSON object.   python tools/parity_full_config2.py [n [damping]]
 """
 import faulthandler, json, os, sys, time, warnings
 faulthandler.enable()
@@ -15,7 +15,8 @@ import verde_oracle as vo
 import verde_b200 as vb
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000
-damping, mindist = 1e-6, 1e-5
+damping = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-6
+mindist = 1e-5
 tab = vb.CheckerBoard().scatter(size=n, random_state=0)
 e, nn, d = tab.easting.values, tab.northing.values, tab.scalars.values
 out = {"n": n, "damping": damping, "mindist": mindist, "host_cores": os.cpu_count()}
