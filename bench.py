@@ -37,7 +37,28 @@ import threading
 import time
 import warnings
 
-import numpy as np
+
+def _wants_reference_arm(argv):
+    return any(a == "reference" or a.endswith("=reference") for a in argv)
+
+
+def host_cores():
+    "Cores this process may run on (the launcher's affinity mask, not the machine's core count)."
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank it starts.  The CPU arm must use ALL host
+# cores however it was launched, and OpenBLAS / libgomp read these variables when they are loaded -- so they
+# are set here, before numpy is imported (force_cpu_threads() repeats it at run time through threadpoolctl
+# for libraries a site hook may have loaded earlier).
+if _wants_reference_arm(sys.argv[1:]):
+    for _var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_var] = str(host_cores())
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -178,34 +199,74 @@ def cpu_reference_step(sample_n, sample_grid, full):
     }
 
 
+def force_cpu_threads():
+    """
+    Make BLAS/LAPACK and the oracle's OpenMP kernels use every host core regardless of the launcher
+    (torchrun sets OMP_NUM_THREADS=1) and report the thread counts actually in force.
+    """
+    cores = host_cores()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import verde_oracle as vo
+
+    vo._lib()  # load the OpenMP Green's kernels first so that threadpoolctl sees their libgomp
+    pools = {}
+    try:
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(limits=cores)
+        for pool in threadpoolctl.threadpool_info():
+            pools["{}:{}".format(pool.get("user_api"), pool.get("internal_api"))] = pool.get("num_threads")
+    except ImportError:  # pragma: no cover
+        pools["threadpoolctl"] = "missing"
+    return cores, pools
+
+
+def reference_sample_plan(args):
+    """
+    The CPU arm times a bounded sample (n = m = --cpu-sample, ~35 s on 16 cores at the default 20 000)
+    and repeats it while the wall-clock budget lasts: at least 3, at most --steps samples; the value printed
+    is the MEDIAN over those samples.
+    """
+    return max(1, min(args.steps, 3)), args.steps, float(args.cpu_budget)
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     n = 50_000 * world
     m = 50_000
     npts = 2000 * 2000 * world
-    cores = os.cpu_count() or 1
+    cores, pools = force_cpu_threads()
     sample_n, sample_grid = args.cpu_sample, 150
-    for _ in range(args.warmup):
+    for _ in range(max(1, min(args.warmup, 2))):
         cpu_reference_step(min(1500, sample_n), 40, (n, m, npts))
-    times, last = [], None
-    for _ in range(args.steps):
+    at_least, at_most, budget = reference_sample_plan(args)
+    times, samples = [], []
+    t_begin = time.perf_counter()
+    while len(samples) < at_most:
         t0 = time.perf_counter()
-        last = cpu_reference_step(sample_n, sample_grid, (n, m, npts))
+        samples.append(cpu_reference_step(sample_n, sample_grid, (n, m, npts)))
         times.append(time.perf_counter() - t0)
+        if len(samples) >= at_least and (time.perf_counter() - t_begin) + times[-1] > budget:
+            break
+    order = sorted(range(len(samples)), key=lambda i: samples[i]["value"])
+    mid = samples[order[len(order) // 2]]  # the median sample (upper median for an even count)
+    values = [x["value"] for x in samples]
     sample = ("oracle (C/OpenMP Green's kernels + numpy/scipy BLAS/LAPACK normal equations) on n=m={} "
               "points and a {}x{} grid; extrapolated to n={}, m={}, {} grid points with n*m, n*m^2, "
-              "m^3/3 and N*M scaling").format(sample_n, sample_grid, sample_grid, n, m, npts)
+              "m^3/3 and N*M scaling; median of {} samples").format(sample_n, sample_grid, sample_grid, n, m, npts,
+                                                                   len(samples))
     line = {
-        "impl": "reference", "metric": METRIC, "value": last["value"], "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (last["fit_s_extrapolated"] + last["predict_s_extrapolated"]),
+        "impl": "reference", "metric": METRIC, "value": mid["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (mid["fit_s_extrapolated"] + mid["predict_s_extrapolated"]),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
-        "fit_s": last["fit_s_extrapolated"], "predict_gpts_per_s": npts / last["predict_s_extrapolated"] * 1e-9,
-        "cpu_baseline": {"value": last["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "sample_wall_s": statistics.mean(times), "phases_s": last["phases_s"],
+        "fit_s": mid["fit_s_extrapolated"], "predict_gpts_per_s": npts / mid["predict_s_extrapolated"] * 1e-9,
+        "cpu_baseline": {"value": mid["value"], "unit": UNIT, "cores": cores, "threads": pools, "kind": "port",
+                         "sample": sample, "samples_timed": len(samples), "sample_wall_s": statistics.median(times),
+                         "values_min_max": [min(values), max(values)], "phases_s": mid["phases_s"],
                          "extrapolated": True},
-        "e2e": {"value": last["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": mid["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -242,7 +303,9 @@ def main():
     ap.add_argument("--forces", type=int, default=None,
                     help="number of forces (default: forces at the data on one GPU, 50000 separate forces on several); "
                          "--gpus 1 --size 400000 --forces 50000 --grid 10000 is BASELINE configs[2] on ONE GPU")
-    ap.add_argument("--cpu-sample", type=int, default=14000, help="n=m of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="n=m of the CPU baseline sample")
+    ap.add_argument("--cpu-budget", type=float, default=200.0,
+                    help="--impl reference: wall-clock seconds after which no further sample is started")
     ap.add_argument("--cholesky", default="auto", choices=["auto", "replicated", "distributed"],
                     help="N > 1: replicated m x m Cholesky on every rank, or panel-cyclic over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -455,10 +518,10 @@ def main():
         "diag_min_max": [phase["info"]["diag_min"], phase["info"]["diag_max"]],
     }
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
+        cores, pools = force_cpu_threads()
         cpu = cpu_reference_step(args.cpu_sample, 150, (n_total, m, npts_total))
         line["cpu_baseline"] = {
-            "value": cpu["value"], "unit": UNIT, "cores": cores, "kind": "port",
+            "value": cpu["value"], "unit": UNIT, "cores": cores, "threads": pools, "kind": "port",
             "sample": ("oracle on n=m={} + 150x150 grid ({:.1f} s of CPU work), extrapolated to the full workload with "
                        "n*m, n*m^2, m^3/3, N*M scaling").format(args.cpu_sample, cpu["sample_seconds"]),
             "fit_s_extrapolated": cpu["fit_s_extrapolated"], "predict_gpairs_per_s": cpu["predict_gpairs_per_s"],

@@ -52,6 +52,15 @@ typedef struct vb200_fit_info {
     int64_t kernel_launches; /* all kernel launches of this fit                                */
     double diag_min;         /* min / max of diag(L)^2: a cheap conditioning indicator         */
     double diag_max;
+    /* --- since ABI version 200 (SURVEY 8b out_diag{cond, backward_err}); 0 when "fit_diagnostics" is off --- */
+    double lambda_max;       /* largest eigenvalue of the damped, column-scaled normal matrix A (power iteration on L L^T) */
+    double lambda_min_est;   /* Rayleigh-quotient estimate (>= the true value) of its smallest eigenvalue (inverse iteration) */
+    double cond_est;         /* lambda_max / lambda_min_est  <= cond_2(A)                       */
+    double cond_upper;       /* lambda_max / damping         >= cond_2(A)  (G is positive semi-definite) */
+    double backward_err;     /* ||Js^T W (d - Js c) - damping c|| / (lambda_max ||c|| + ||Js^T W d||), matrix-free, exact
+                                Green's functions; only the fused fits (vb200_spline_fit*, vb200_least_squares) and
+                                vb200_backward_error fill it, otherwise -1                       */
+    double diag_ms;          /* device + host time spent on these diagnostics                   */
 } vb200_fit_info;
 
 /* ---- library / device -------------------------------------------------------------- */
@@ -62,7 +71,8 @@ int vb200_set_device(int device);
 /* tunables: "predict_exact" (0/1), "chol_panel_tiles" (1..16), "gram_slab_chunks" (1..16),
  * "gram_fused" (0/1: generate Jacobian rows in shared memory inside the Gram kernel instead of staging
  * a panel), "gemm_variant" (0/1/2/3), "gemm_strip", "predict_pts", "predict_minb", "predict_wide" (0/1),
- * "sweep_group" (systems per batch of vb200_gram_solve_multi, 0 = as many as fit), "solve_variant" */
+ * "sweep_group" (systems per batch of vb200_gram_solve_multi, 0 = as many as fit), "solve_variant",
+ * "fit_diagnostics" (0/1, default 1: condition estimate + backward error after every fit) */
 int vb200_set_option(const char *key, double value);
 /* frees the cached device workspace (Gram matrix, panels) */
 int vb200_release_workspace(void);
@@ -189,6 +199,20 @@ int vb200_jacobian_transpose_apply(const double *east, const double *north, int6
                                    const double *force_east, const double *force_north, int64_t m,
                                    double mindist, const double *v, double *out);
 
+/* Diagnostics for the staged (multi-GPU) fit, SURVEY 8b out_diag{cond, backward_err}:
+ * vb200_normal_residual: grad = J^T W (d - J force) over THIS caller's rows, matrix-free with the exact Green's
+ *         functions (kind 0 scalar / 1 elastic, as vb200_gram_accumulate; data and weights stacked for kind 1;
+ *         grad has m or 2m entries, host or device).  Ranks sum their partial gradients (m doubles).
+ * vb200_backward_error: eta = ||D grad - damping c|| / (lambda_max ||c|| + ||D J^T W d||), c = force / D, from
+ *         the summed gradient, the all-reduced statistics vector of vb200_gram_accumulate and lambda_max of
+ *         vb200_fit_info; the same quantity the fused fits report as vb200_fit_info.backward_err. */
+int vb200_normal_residual(int kind, const double *east, const double *north, const double *data,
+                          const double *weights, int64_t n, const double *force_east,
+                          const double *force_north, int64_t m, double mindist, double poisson,
+                          const double *force, double *grad);
+int vb200_backward_error(const double *grad, const double *stats_dev, int64_t cols, int64_t total_rows,
+                         double damping, const double *force, double lambda_max, double *eta);
+
 /* ---- either side of the spline path ---------------------------------
  * block_split: replaces verde/coordinates.py:848-946 block_split(coordinates, ...): every point gets the
  *         index of the nearest block centre, label = i_north * n_east + i_east over the centre grid the
@@ -211,6 +235,9 @@ int vb200_jacobian_transpose_apply(const double *east, const double *north, int6
 #define VB200_REDUCE_WMEAN 7     /* numpy.average(values, weights=w) */
 #define VB200_REDUCE_WVAR 8      /* numpy.average((values - wmean)**2, weights=w) */
 #define VB200_REDUCE_INV_SUM_W 9 /* 1 / sum(w) */
+#define VB200_REDUCE_VAR0 10     /* population variance, ddof = 0 (numpy.var applied as a callable, pandas >= 3) */
+#define VB200_REDUCE_STD 11      /* sample standard deviation, ddof = 1 (pandas "std") */
+#define VB200_REDUCE_STD0 12     /* population standard deviation, ddof = 0 (numpy.std) */
 int vb200_block_split(const double *east, const double *north, int64_t n, const double *centers_east,
                       int32_t n_east, const double *centers_north, int32_t n_north, int64_t *labels,
                       int64_t *n_blocks);

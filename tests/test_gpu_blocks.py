@@ -130,6 +130,13 @@ def test_block_reduce_vs_oracle_shapes(vb, bo, n, shape):
     np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-13 * np.abs(d).max())
     _, got = vb.BlockReduce("count", shape=shape, region=region).filter((e, nn), d)
     np.testing.assert_array_equal(got, np.bincount(ref_labels)[ids])
+    # numpy callables are applied as they are (ddof = 0, pandas >= 3); the pandas names mean ddof = 1
+    small = d / np.abs(d).max()
+    for red, ref_fn in ((np.var, np.var), (np.std, np.std), ("var", bo.sample_variance),
+                        ("std", lambda v: np.sqrt(bo.sample_variance(v)))):
+        _, got = vb.BlockReduce(red, shape=shape, region=region).filter((e, nn), small)
+        _, ref = bo.group_reduce(ref_labels, small, ref_fn)
+        np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-15)
 
 
 def test_block_reduce_edge_cases(vb, bo):

@@ -87,8 +87,9 @@ def test_reduction_mapping_and_errors():
     assert br.reduction_code("var") == br.VAR and br.reduction_code("count") == br.COUNT
     with pytest.raises(NotImplementedError):
         br.reduction_code(lambda x: x.mean())
-    with pytest.raises(NotImplementedError):
-        br.reduction_code(np.var)  # numpy's ddof=0 variance is not pandas' "var"
+    # pandas >= 3 applies a numpy callable as it is: np.var / np.std are ddof = 0, the names "var" / "std" ddof = 1
+    assert br.reduction_code(np.var) == br.VAR0 and br.reduction_code(np.std) == br.STD0
+    assert br.reduction_code("std") == br.STD
     with pytest.raises(TypeError):
         br.reduction_code(np.mean, weighted=True)
     w = br.variance_to_weights(np.array([0, 2, 0.2, 1e-16, np.nan]))

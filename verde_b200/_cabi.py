@@ -37,6 +37,12 @@ class FitInfo(ctypes.Structure):
         ("kernel_launches", ctypes.c_int64),
         ("diag_min", ctypes.c_double),
         ("diag_max", ctypes.c_double),
+        ("lambda_max", ctypes.c_double),
+        ("lambda_min_est", ctypes.c_double),
+        ("cond_est", ctypes.c_double),
+        ("cond_upper", ctypes.c_double),
+        ("backward_err", ctypes.c_double),
+        ("diag_ms", ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -79,6 +85,8 @@ SIGNATURES = {
     "vb200_gram_factor": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_chol_solve": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [ctypes.POINTER(FitInfo)]),
     "vb200_jacobian_transpose_apply": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl] + [ctypes.c_void_p] * 2),
+    "vb200_normal_residual": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl] + [ctypes.c_void_p] * 2),
+    "vb200_backward_error": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_void_p, dbl, ctypes.POINTER(dbl)]),
     "vb200_least_squares": (ctypes.c_int, [ctypes.c_void_p, i64, i64] + [ctypes.c_void_p] * 2 + [dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
 }
 
@@ -133,11 +141,8 @@ def f64(a):
     return np.ascontiguousarray(np.ravel(np.atleast_1d(np.asarray(a))), dtype=np.float64)
 
 
-def check(rc, what):
-    """Translate a status code: <0 -> EngineError, >0 -> LinAlgError, 0 -> ok."""
-    if rc == 0:
-        return
-    msg = load().vb200_last_error().decode("utf-8", "replace")
+def raise_status(rc, what, msg):
+    """Raise the exception a non-zero status code stands for: <0 -> EngineError family, >0 -> LinAlgError."""
     if rc > 0:
         raise np.linalg.LinAlgError(
             "{}: the damped normal matrix is not positive definite (pivot {}): {}".format(what, rc, msg)
@@ -147,3 +152,10 @@ def check(rc, what):
     if rc == E_BADARG:
         raise ValueError("{}: {}".format(what, msg))
     raise EngineError("{}: {}".format(what, msg))
+
+
+def check(rc, what):
+    """Translate a status code: <0 -> EngineError, >0 -> LinAlgError, 0 -> ok."""
+    if rc == 0:
+        return
+    raise_status(rc, what, load().vb200_last_error().decode("utf-8", "replace"))

@@ -15,8 +15,13 @@ The reference accepts ANY Python callable as *reduction* (pandas calls it once
 per block on the host).  A device path can only offer a closed set; it covers
 the reductions Verde's documentation and tests use -- ``np.mean`` / ``"mean"``,
 ``np.average`` (weighted when weights are given), ``np.median``, ``np.sum``,
-``np.min``, ``np.max``, ``"count"``, ``np.var`` / ``"var"`` (pandas' ddof=1) --
-and raises ``NotImplementedError`` for anything else (no CPU fallback).
+``np.min``, ``np.max``, ``"count"``, ``"var"`` / ``"std"`` (pandas' ddof=1) and the callables ``np.var`` /
+``np.std`` (ddof=0: pandas >= 3 applies a numpy callable as it is, which is what the pinned reference
+environment does) -- and raises ``NotImplementedError`` for anything else (no CPU fallback).
+
+NaN values: every device reduction propagates NaN (a block containing one gives NaN).  pandas routes some
+numpy callables to its own NaN-skipping methods (``np.mean``, ``np.sum``, ``np.min``, ``np.max`` under
+pandas 3) and not others (``np.median``); that version-dependent behaviour is not reproduced.
 """
 import ctypes
 
@@ -27,10 +32,12 @@ from . import _cabi
 from .base import check_coordinates, check_fit_input
 from .coords import get_region, grid_coordinates
 
-MEAN, SUM, MIN, MAX, COUNT, MEDIAN, VAR, WMEAN, WVAR, INV_SUM_W = range(10)
+MEAN, SUM, MIN, MAX, COUNT, MEDIAN, VAR, WMEAN, WVAR, INV_SUM_W, VAR0, STD, STD0 = range(13)
 
 _BY_NAME = {"mean": MEAN, "average": MEAN, "sum": SUM, "min": MIN, "amin": MIN, "max": MAX, "amax": MAX,
-            "count": COUNT, "size": COUNT, "median": MEDIAN, "var": VAR}
+            "count": COUNT, "size": COUNT, "median": MEDIAN, "var": VAR, "std": STD}
+# numpy callables whose pandas-name twin means something else (ddof = 1): applied as they are (ddof = 0)
+_NUMPY_CALLABLE = {"var": VAR0, "std": STD0}
 
 
 def reduction_code(reduction, weighted=False):
@@ -47,11 +54,13 @@ def reduction_code(reduction, weighted=False):
             "weights were given, so the reduction must accept a 'weights' argument: only numpy.average "
             "does among the device reductions (got {!r})".format(reduction)
         )
-    if name in _BY_NAME and not (name == "var" and not isinstance(reduction, str)):
+    if not isinstance(reduction, str) and name in _NUMPY_CALLABLE:
+        return _NUMPY_CALLABLE[name]
+    if name in _BY_NAME:
         return _BY_NAME[name]
     raise NotImplementedError(
-        "reduction {!r} has no device implementation (available: numpy mean, average, median, sum, min, max "
-        "or the pandas names 'mean', 'median', 'sum', 'min', 'max', 'count', 'var'); arbitrary Python "
+        "reduction {!r} has no device implementation (available: numpy mean, average, median, sum, min, max, var, "
+        "std or the pandas names 'mean', 'median', 'sum', 'min', 'max', 'count', 'var', 'std'); arbitrary Python "
         "callables would need the host groupby this path replaces".format(reduction)
     )
 

@@ -8,7 +8,9 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <utility>
@@ -47,6 +49,7 @@ struct Options {
     int gram_slab_chunks = 16;
     int gram_fused = 0;
     int sweep_group = 0;  // damped systems factored side by side in vb200_gram_solve_multi (0 = as many as fit)
+    int fit_diagnostics = 1;  // condition estimate + backward error after every fit (vb_diag.cu)
 } g_opt;
 
 // ---- cached workspace (grow-only, per process; one process per GPU) --------------------
@@ -285,6 +288,121 @@ __global__ void __launch_bounds__(256) vb_peak_dfma_kernel(double *out, double a
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// ---- per-fit diagnostics (kernels in vb_diag.cu) -------------------------------------------------------
+double wall_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+// condition estimate of A = L L^T (every solve path leaves L in `L`); fills the cond fields of *info
+int diag_condition(const double *L, int T, long long cols, double damping, vb200_fit_info *info, cudaStream_t st)
+{
+    if (!info || !g_opt.fit_diagnostics) return 0;
+    const double t0 = wall_ms();
+    double *scratch;
+    int *d_flags;
+    CU(ws_get("diag_scratch", sizeof(double) * (size_t)vb_diag_scratch_doubles(T), (void **)&scratch));
+    CU(ws_get("sweep_flags", sizeof(int) * 2 * T, (void **)&d_flags));
+    VbCondEstimate ce;
+    const long long launches0 = vb_launch_counter;
+    CU(vb_cond_estimate(L, T, cols, scratch, d_flags, st, 30, 8, &ce));
+    info->lambda_max = ce.lambda_max;
+    info->lambda_min_est = ce.lambda_min;
+    info->cond_est = ce.lambda_min > 0.0 ? ce.lambda_max / ce.lambda_min : 0.0;
+    info->cond_upper = damping > 0.0 ? ce.lambda_max / damping : 0.0;
+    info->kernel_launches += vb_launch_counter - launches0;
+    info->diag_ms += wall_ms() - t0;
+    return 0;
+}
+
+// grad = J^T W (d - J force) for the rows of `pb` (all pointers on the device), matrix-free, exact Green's functions
+int normal_residual_dev(const VbGramProblem &pb, const double *force, double *grad, cudaStream_t st)
+{
+    const long long rows = vb_sys_rows(pb), cols = vb_sys_cols(pb);
+    double *pred, *resid;
+    CU(ws_get("diag_pred", sizeof(double) * (size_t)(rows > 0 ? rows : 1), (void **)&pred));
+    CU(ws_get("diag_resid", sizeof(double) * (size_t)(rows > 0 ? rows : 1), (void **)&resid));
+    if (rows == 0) {
+        CU(cudaMemsetAsync(grad, 0, sizeof(double) * cols, st));
+        return 0;
+    }
+    int pts, nsplit;
+    double *scratch = nullptr;
+    if (pb.kind == 2) {
+        CU(vb_launch_gemv(pb.jac, rows, cols, force, 0, pred, st));
+        CU(vb_launch_weighted_residual(pb.data, pred, pb.weights, rows, resid, st));
+        CU(vb_launch_gemv(pb.jac, rows, cols, resid, 1, grad, st));
+    } else if (pb.kind == 0) {
+        vb_predict_plan(pb.n, pb.m, &pts, &nsplit);
+        if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * (size_t)nsplit * pb.n, (void **)&scratch));
+        CU(vb_launch_predict(pb.east, pb.north, pb.n, pb.fe, pb.fn, force, pb.m, pb.mindist, 1, pts, nsplit, scratch,
+                             pred, st));
+        CU(vb_launch_weighted_residual(pb.data, pred, pb.weights, rows, resid, st));
+        // J^T r: the same kernel with points and forces swapped (g is even in the coordinate differences)
+        vb_predict_plan(pb.m, pb.n, &pts, &nsplit);
+        scratch = nullptr;
+        if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * (size_t)nsplit * pb.m, (void **)&scratch));
+        CU(vb_launch_predict(pb.fe, pb.fn, pb.m, pb.east, pb.north, resid, pb.n, pb.mindist, 1, pts, nsplit, scratch,
+                             grad, st));
+    } else {
+        vb_predict_plan(pb.n, pb.m, &pts, &nsplit);
+        if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * 2 * (size_t)nsplit * pb.n, (void **)&scratch));
+        CU(vb_launch_predict2d(pb.east, pb.north, pb.n, pb.fe, pb.fn, force, pb.m, pb.mindist, pb.poisson, 1, pts, nsplit,
+                               scratch, pred, pred + pb.n, st));
+        CU(vb_launch_weighted_residual(pb.data, pred, pb.weights, rows, resid, st));
+        // the block Jacobian [[ee, ne], [ne, nn]] is symmetric under the swap of points and forces as well
+        vb_predict_plan(pb.m, pb.n, &pts, &nsplit);
+        scratch = nullptr;
+        if (nsplit > 1) CU(ws_get("pred_split", sizeof(double) * 2 * (size_t)nsplit * pb.m, (void **)&scratch));
+        CU(vb_launch_predict2d(pb.fe, pb.fn, pb.m, pb.east, pb.north, resid, pb.n, pb.mindist, pb.poisson, 1, pts, nsplit,
+                               scratch, grad, grad + pb.m, st));
+    }
+    return 0;
+}
+
+// eta from the summed gradient (all device pointers); synchronises the stream
+int backward_error_dev(const double *grad, const double *jtwd, const double *inv_scale, const double *force,
+                       long long cols, double damping, double lambda_max, double *eta, cudaStream_t st)
+{
+    double *d3, h3[3] = {0, 0, 0};
+    CU(ws_get("diag_norms", sizeof(double) * 3, (void **)&d3));
+    CU(vb_launch_backward_norms(grad, jtwd, inv_scale, force, cols, damping, d3, st));
+    CU(cudaMemcpyAsync(h3, d3, sizeof(h3), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double den = lambda_max * sqrt(h3[1]) + sqrt(h3[2]);
+    *eta = den > 0.0 ? sqrt(h3[0]) / den : 0.0;
+    return 0;
+}
+
+VbGramProblem g_last_problem = {};  // the inputs of the last vb200_gram_accumulate, as device pointers
+
+// stages (host pointers) or passes through (device pointers) the inputs of a fit into *pb
+int stage_problem(int kind, const double *jac, const double *east, const double *north, const double *data,
+                  const double *weights, int64_t n, const double *force_east, const double *force_north, int64_t m,
+                  double mindist, double poisson, VbGramProblem *pb, cudaStream_t st)
+{
+    *pb = VbGramProblem{};
+    pb->kind = kind;
+    pb->n = n;
+    pb->m = m;
+    pb->mindist = mindist;
+    pb->poisson = poisson;
+    const long long rows = vb_sys_rows(*pb), cols = vb_sys_cols(*pb);
+    if (kind == 2) {
+        CU(stage_in("in_jac", jac, rows * cols, &pb->jac, st));
+    } else {
+        CU(stage_in("in_e", east, n, &pb->east, st));
+        CU(stage_in("in_n", north, n, &pb->north, st));
+        CU(stage_in("in_fe", force_east, m, &pb->fe, st));
+        CU(stage_in("in_fn", force_north, m, &pb->fn, st));
+    }
+    CU(stage_in("in_d", data, rows, &pb->data, st));
+    CU(stage_in("in_w", weights, rows, &pb->weights, st));
+    return 0;
+}
 }  // namespace
 
 // vb_chol.cu calls the GEMM through this hook so that its launches are timed too.
@@ -292,7 +410,7 @@ cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t st) { return ti
 
 extern "C" {
 
-int vb200_version(void) { return 100; }
+int vb200_version(void) { return 200; }
 const char *vb200_last_error(void) { return g_error.c_str(); }
 
 int vb200_device_count(void)
@@ -322,6 +440,7 @@ int vb200_set_option(const char *key, double value)
     else if (k == "trsm_tiles") vb_trsm_tiles = (int)value;
     else if (k == "gram_fused") g_opt.gram_fused = value != 0.0;
     else if (k == "sweep_group") g_opt.sweep_group = value < 0 ? 0 : (int)value;
+    else if (k == "fit_diagnostics") g_opt.fit_diagnostics = value != 0.0;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
     else if (k == "predict_minb") vb_predict_minb = (int)value;
@@ -537,25 +656,16 @@ static int gram_accumulate_impl(int kind, const double *jac, const double *east,
     if (n > 0 && (!data || (kind != 2 && (!east || !north)))) return fail(VB200_E_BADARG, "null data pointer");
     if (kind != 2 && (!force_east || !force_north)) return fail(VB200_E_BADARG, "null force coordinates");
     cudaStream_t st = 0;
-    VbGramProblem pb = {};
-    pb.kind = kind;
-    pb.n = n;
-    pb.m = m;
-    pb.mindist = mindist;
-    pb.poisson = poisson;
+    VbGramProblem pb;
+    {
+        const int rc = stage_problem(kind, jac, east, north, data, weights, n, force_east, force_north, m, mindist,
+                                     poisson, &pb, st);
+        if (rc != 0) return rc;
+    }
+    g_last_problem = pb;
     const long long rows = vb_sys_rows(pb), cols = vb_sys_cols(pb);
     const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
     const long long Mpad = (long long)T * VB_TILE;
-    if (kind == 2) {
-        CU(stage_in("in_jac", jac, rows * cols, &pb.jac, st));
-    } else {
-        CU(stage_in("in_e", east, n, &pb.east, st));
-        CU(stage_in("in_n", north, n, &pb.north, st));
-        CU(stage_in("in_fe", force_east, m, &pb.fe, st));
-        CU(stage_in("in_fn", force_north, m, &pb.fn, st));
-    }
-    CU(stage_in("in_d", data, rows, &pb.data, st));
-    CU(stage_in("in_w", weights, rows, &pb.weights, st));
 
     if (info) {
         info->block_rows = T;
@@ -711,7 +821,8 @@ int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, in
         fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
         return h_info;
     }
-    return 0;
+    if (info) info->backward_err = -1.0;
+    return diag_condition(L, T, cols, damping, info, st);
 }
 
 int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
@@ -823,6 +934,7 @@ struct StepState {
     bool open = false;
     int T = 0;
     long long cols = 0;
+    double damping = 0.0;
     Span fac;
     long long launches0 = 0;
 } g_step;
@@ -847,6 +959,7 @@ int vb200_chol_begin(double *gram_dev, const double *stats_dev, int64_t cols, in
     g_step.open = true;
     g_step.T = T;
     g_step.cols = cols;
+    g_step.damping = damping;
     g_step.launches0 = vb_launch_counter;
     CU(span_begin(&g_step.fac, st));
     CU(cudaMemsetAsync(d_info, 0, sizeof(int), st));
@@ -933,7 +1046,8 @@ int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, 
         fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
         return h_info;
     }
-    return 0;
+    if (info) info->backward_err = -1.0;
+    return diag_condition(chol_dev, T, cols, g_step.damping, info, st);
 }
 
 // ---- block reductions and the distance mask (kernels in vb_block.cu) -------
@@ -1037,7 +1151,7 @@ int vb200_block_aggregate(const double *values, const double *weights, int64_t n
 {
     if (!g_block.open) return fail(VB200_E_BADARG, "vb200_block_split was not called");
     if (n != g_block.n) return fail(VB200_E_BADARG, "values must have one entry per point of the last vb200_block_split (%lld given, %lld expected)", (long long)n, g_block.n);
-    if (op < VB_REDUCE_MEAN || op > VB_REDUCE_INV_SUM_W) return fail(VB200_E_BADARG, "unknown reduction %d", (int)op);
+    if (op < VB_REDUCE_MEAN || op > VB_REDUCE_LAST) return fail(VB200_E_BADARG, "unknown reduction %d", (int)op);
     if (g_block.nseg == 0) return 0;
     const bool needs_w = op == VB_REDUCE_WMEAN || op == VB_REDUCE_WVAR || op == VB_REDUCE_INV_SUM_W;
     const bool needs_v = op != VB_REDUCE_COUNT && op != VB_REDUCE_INV_SUM_W;
@@ -1101,7 +1215,9 @@ int vb200_distance_mask(const double *data_east, const double *data_north, int64
         if (!(xmax >= xmin) || !(ymax >= ymin) || !(xmax - xmin < 1e300) || !(ymax - ymin < 1e300))
             return fail(VB200_E_BADARG, "data coordinates must be finite");
         const double extent = (xmax - xmin) > (ymax - ymin) ? (xmax - xmin) : (ymax - ymin);
-        double pitch = maxdist > 0.0 ? maxdist : 0.0;
+        // a hair wider than maxdist: the cell index is (int)((x - x0) * (1 / pitch)) with two roundings, and a data
+        // point and a node at distance <= maxdist must never land two cells apart (3 x 3 scan)
+        double pitch = maxdist > 0.0 ? maxdist * (1.0 + 1e-9) : 0.0;
         if (pitch < extent / 4096.0) pitch = extent / 4096.0;
         if (!(pitch > 0.0) || !(pitch < 1e300)) pitch = 1.0;
         const int nx = (int)((xmax - xmin) / pitch) + 1, ny = (int)((ymax - ymin) / pitch) + 1;
@@ -1173,7 +1289,8 @@ int vb200_gram_factor(double *gram_dev, const double *stats_dev, int64_t cols, i
         fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
         return h_info;
     }
-    return 0;
+    if (info) info->backward_err = -1.0;
+    return diag_condition(gram_dev, T, cols, damping, info, st);
 }
 
 int vb200_chol_solve(const double *chol_dev, const double *inv_scale_dev, int64_t cols, const double *rhs,
@@ -1260,7 +1377,74 @@ static int fit_impl(int kind, const double *jac, const double *east, const doubl
     int rc = gram_accumulate_impl(kind, jac, east, north, data, weights, n, force_east, force_north, m,
                                   mindist, poisson, G, stats, 0, info);
     if (rc != 0) return rc;
-    return vb200_gram_solve(G, stats, cols, rows, damping, 0, out_force, info);
+    rc = vb200_gram_solve(G, stats, cols, rows, damping, 0, out_force, info);
+    if (rc != 0 || !info || !g_opt.fit_diagnostics) return rc;
+    // backward error of the forces just computed (the inputs are still staged in their workspace slots)
+    const double t0 = wall_ms();
+    const long long launches0 = vb_launch_counter;
+    cudaStream_t st = 0;
+    const VbGramProblem pb = g_last_problem;  // device pointers staged by gram_accumulate_impl just above
+    const double *force_dev = out_force;
+    if (!is_device_ptr(out_force)) {
+        void *staged;
+        CU(ws_get("out_params", sizeof(double) * cols, &staged));  // vb200_gram_solve's staging copy
+        force_dev = static_cast<const double *>(staged);
+    }
+    double *grad, *inv_scale;
+    CU(ws_get("diag_grad", sizeof(double) * cols, (void **)&grad));
+    CU(ws_get("inv_scale", sizeof(double) * vb200_padded_cols(cols), (void **)&inv_scale));
+    rc = normal_residual_dev(pb, force_dev, grad, st);
+    if (rc != 0) return rc;
+    rc = backward_error_dev(grad, stats, inv_scale, force_dev, cols, damping, info->lambda_max, &info->backward_err, st);
+    info->kernel_launches += vb_launch_counter - launches0;
+    info->diag_ms += wall_ms() - t0;
+    return rc;
+}
+
+int vb200_normal_residual(int kind, const double *east, const double *north, const double *data,
+                          const double *weights, int64_t n, const double *force_east,
+                          const double *force_north, int64_t m, double mindist, double poisson,
+                          const double *force, double *grad)
+{
+    if (kind != 0 && kind != 1) return fail(VB200_E_BADARG, "kind must be 0 (scalar) or 1 (elastic 2-D)");
+    if (n < 0 || m <= 0) return fail(VB200_E_BADARG, "bad sizes n=%lld m=%lld", (long long)n, (long long)m);
+    if (!force_east || !force_north || !force || !grad || (n > 0 && (!east || !north || !data)))
+        return fail(VB200_E_BADARG, "null pointer");
+    if (n > 0x7fffffffLL || m > 0x3fffffffLL) return fail(VB200_E_BADARG, "too many points");
+    cudaStream_t st = 0;
+    VbGramProblem pb;
+    int rc = stage_problem(kind, nullptr, east, north, data, weights, n, force_east, force_north, m, mindist, poisson,
+                           &pb, st);
+    if (rc != 0) return rc;
+    const long long cols = vb_sys_cols(pb);
+    const double *dforce;
+    CU(stage_in("in_f", force, cols, &dforce, st));
+    OutBuf ob;
+    CU(stage_out("diag_grad", grad, cols, &ob));
+    rc = normal_residual_dev(pb, dforce, ob.dev, st);
+    if (rc != 0) return rc;
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vb200_backward_error(const double *grad, const double *stats_dev, int64_t cols, int64_t total_rows,
+                         double damping, const double *force, double lambda_max, double *eta)
+{
+    if (cols <= 0 || total_rows <= 0) return fail(VB200_E_BADARG, "bad sizes");
+    if (!grad || !stats_dev || !force || !eta) return fail(VB200_E_BADARG, "null pointer");
+    if (!is_device_ptr(stats_dev)) return fail(VB200_E_BADARG, "stats buffer must be device memory");
+    cudaStream_t st = 0;
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    const long long Mpad = (long long)T * VB_TILE;
+    const double *dgrad, *dforce;
+    CU(stage_in("diag_grad_in", grad, cols, &dgrad, st));
+    CU(stage_in("in_f", force, cols, &dforce, st));
+    double *inv_scale, *rhs;
+    CU(ws_get("diag_inv_scale", sizeof(double) * Mpad, (void **)&inv_scale));
+    CU(ws_get("diag_rhs", sizeof(double) * Mpad, (void **)&rhs));
+    CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale, rhs, st));
+    return backward_error_dev(dgrad, stats_dev, inv_scale, dforce, cols, damping, lambda_max, eta, st);
 }
 
 int vb200_spline_fit(const double *east, const double *north, const double *data,

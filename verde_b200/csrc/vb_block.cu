@@ -432,7 +432,11 @@ vb_block_aggregate_kernel(const unsigned *__restrict__ perm, const unsigned *__r
                     s2.add(weighted ? w[i] * dlt * dlt : dlt * dlt);
                 }
                 const double t2 = group_sum<GROUP>(s2.value(), sh);
-                res = weighted ? t2 / tw : t2 / (cnt - 1.0);  // pandas var: ddof = 1 (NaN for single points)
+                // pandas "var"/"std": ddof = 1 (NaN for single points); the numpy callables np.var / np.std, which
+                // pandas >= 3 applies as they are: ddof = 0
+                const bool population = (op == VB_REDUCE_VAR0 || op == VB_REDUCE_STD0);
+                res = weighted ? t2 / tw : t2 / (population ? cnt : cnt - 1.0);
+                if (op == VB_REDUCE_STD || op == VB_REDUCE_STD0) res = sqrt(res);
             }
         }
     }

@@ -406,12 +406,8 @@ cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, 
     int potrf_smem, trsm_smem;
     if ((err = chol_set_attributes(&potrf_smem, &trsm_smem)) != cudaSuccess) return err;
     if (batch < 1) batch = 1;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
-    }
+    int sms = 0;
+    if ((err = vb_sm_count(&sms)) != cudaSuccess) return err;
     for (int kk = 0; kk < pw; ++kk) {
         const int k = k0 + kk;
         vb_potrf_tile_kernel<<<batch, POTRF_THREADS, potrf_smem, stream>>>(

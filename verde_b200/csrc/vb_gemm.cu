@@ -599,6 +599,21 @@ vb_fused_gram_kernel(const VbFusedGramParams p, long long ntiles, const double2 
 }  // namespace
 
 long long vb_launch_counter = 0;
+
+cudaError_t vb_sm_count(int *sms)
+{
+    static int cached[256] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 256 && cached[dev] > 0) {
+        *sms = cached[dev];
+        return cudaSuccess;
+    }
+    if ((e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (dev >= 0 && dev < 256) cached[dev] = *sms;
+    return cudaSuccess;
+}
 // 0: v1 (cp.async + __syncthreads); 1: v2 (TMA bulk + mbarrier + bulk reduce), 8 consumer warps;
 // 2: v2 with 16 consumer warps (32x32 warp tiles); 3: v3 persistent (producer run-ahead, RED epilogue)
 int vb_gemm_variant = 3;
@@ -637,12 +652,8 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
         if (e != cudaSuccess) return e;
         vb_gemm_tma_kernel<8><<<(unsigned)tiles, 8 * 32 + 32, V2_SMEM_BYTES, stream>>>(p);
     } else if (vb_gemm_variant == 3) {
-        static int sms = 0;
-        if (sms == 0) {
-            int dev = 0;
-            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        }
+        int sms = 0;
+        if ((e = vb_sm_count(&sms)) != cudaSuccess) return e;
         e = cudaFuncSetAttribute(vb_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         const long long all_tiles = tiles * (p.batch > 1 ? p.batch : 1);

@@ -336,7 +336,9 @@ __global__ void vb_reduce_splits_kernel(const double *__restrict__ part, long lo
 // ---------------------------------------------------------------------------
 // host-side launchers (device pointers)
 // ---------------------------------------------------------------------------
-static int g_tables_ready = 0;
+// one copy of the __device__ table exists PER DEVICE: readiness is tracked per device ordinal so that a process
+// which switches devices (vb200_set_device / torch.cuda.set_device) never reads an all-zero table
+static unsigned long long g_tables_ready_mask[4] = {0, 0, 0, 0};  // up to 256 devices
 
 const double2 *vb_logtab_device_ptr()
 {
@@ -347,7 +349,11 @@ const double2 *vb_logtab_device_ptr()
 
 cudaError_t vb_init_tables()
 {
-    if (g_tables_ready) return cudaSuccess;
+    int dev = 0;
+    cudaError_t derr = cudaGetDevice(&dev);
+    if (derr != cudaSuccess) return derr;
+    const bool tracked = dev >= 0 && dev < 256;
+    if (tracked && (g_tables_ready_mask[dev >> 6] >> (dev & 63)) & 1ull) return cudaSuccess;
     double2 h[VB_LOGTAB_ENTRIES];
     for (int i = 0; i < VB_LOGTAB_ENTRIES; ++i) {
         const long double c = 1.0L + ((long double)i + 0.5L) / VB_LOGTAB_ENTRIES;
@@ -356,7 +362,7 @@ cudaError_t vb_init_tables()
         h[i].y = (double)(-logl((long double)rc));
     }
     cudaError_t err = cudaMemcpyToSymbol(vb_logtab_global, h, sizeof(h));
-    if (err == cudaSuccess) g_tables_ready = 1;
+    if (err == cudaSuccess && tracked) g_tables_ready_mask[dev >> 6] |= 1ull << (dev & 63);
     return err;
 }
 

@@ -33,6 +33,8 @@ long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
 cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream);
 // same, but recorded by the API layer's CUDA-event profile (vb_api.cu)
 cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t stream);
+// SM count of the CURRENT device (cached per device ordinal: a process may switch devices)
+cudaError_t vb_sm_count(int *sms);
 // every kernel launch of the library bumps this (the bench's gpu_launches claim)
 extern long long vb_launch_counter;
 // DMMA tile kernel flavour (see vb_gemm.cu)
@@ -131,6 +133,25 @@ cudaError_t vb_launch_scale_system_batched(const double *G, int T, long long col
                                            long long stride, cudaStream_t stream);
 extern int vb_solve_variant, vb_trsm_tiles;
 
+// ---- per-fit diagnostics (vb_diag.cu) ----------------------------------------------------------------
+struct VbCondEstimate {
+    double lambda_max, lambda_min;  // Rayleigh-quotient estimates of the extreme eigenvalues of L L^T
+    int power_its, inverse_its;
+};
+long long vb_diag_scratch_doubles(int T);
+// flags: 2*T ints (the sweeps' scratch); synchronises the stream (early stopping is decided on the host)
+cudaError_t vb_cond_estimate(const double *L, int T, long long cols, double *scratch, int *flags, cudaStream_t st,
+                             int max_power, int max_inverse, VbCondEstimate *out);
+cudaError_t vb_launch_weighted_residual(const double *d, const double *pred, const double *w, long long n, double *r,
+                                        cudaStream_t st);
+// out3 = {||D grad - damping c||^2, ||c||^2, ||D J^T W d||^2} with c = force / inv_scale
+cudaError_t vb_launch_backward_norms(const double *grad, const double *jtwd, const double *inv_scale,
+                                     const double *force, long long cols, double damping, double *out3,
+                                     cudaStream_t st);
+// explicit row-major (n, m) Jacobian times a vector (transpose = 0) or its transpose times a vector
+cudaError_t vb_launch_gemv(const double *jac, long long n, long long m, const double *v, int transpose, double *out,
+                           cudaStream_t st);
+
 // ---- block reductions and the distance mask (vb_block.cu) --------------------------------------
 // reduction codes of vb200_block_aggregate (mirrored in include/verde_b200.h)
 #define VB_REDUCE_MEAN 0
@@ -143,6 +164,10 @@ extern int vb_solve_variant, vb_trsm_tiles;
 #define VB_REDUCE_WMEAN 7      // sum(w v) / sum(w)          (numpy.average(values, weights=w))
 #define VB_REDUCE_WVAR 8       // sum(w (v - wmean)^2) / sum(w)
 #define VB_REDUCE_INV_SUM_W 9  // 1 / sum(w)                 (propagated uncertainty of a weighted mean)
+#define VB_REDUCE_VAR0 10      // population variance, ddof = 0 (numpy.var as pandas >= 3 applies it)
+#define VB_REDUCE_STD 11       // sample standard deviation, ddof = 1 (pandas "std")
+#define VB_REDUCE_STD0 12      // population standard deviation, ddof = 0 (numpy.std)
+#define VB_REDUCE_LAST VB_REDUCE_STD0
 
 struct VbBlockWorkspace {
     void *keys[2];                 // (label, point index) pairs, ping-pong (uint32 labels; sized for uint64)

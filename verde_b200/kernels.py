@@ -295,28 +295,71 @@ class GramSystem:
                 marks.append((phase, event))
 
         mark("start")
+        # A rank-local failure (bad argument, CUDA error) must not leave the other ranks waiting in the next
+        # broadcast: the first failing status is remembered, this rank stops issuing its own kernels but keeps
+        # taking part in every collective, and all ranks raise together after ``agree_on_status``.
+        status = 0
         for p, (k0, width, owner) in enumerate(schedule):
-            if rank == owner:
-                _cabi.check(lib.vb200_chol_panel(gram_ptr, cols, k0, width), "chol_panel")
+            if rank == owner and status == 0:
+                status = lib.vb200_chol_panel(gram_ptr, cols, k0, width)
             mark("panel")
-            _cabi.check(lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count)),
-                        "chol_panel_range")
+            lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count))
             dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
             mark("broadcast")
             for q0, qwidth, qowner in schedule[p + 1:]:
-                if qowner == rank:
-                    _cabi.check(lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth), "chol_update")
+                if qowner == rank and status == 0:
+                    status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
             mark("update")
         params = np.empty(cols, dtype=np.float64) if out is None else out  # host array or CUDA tensor
+        message = _cabi.load().vb200_last_error().decode("utf-8", "replace") if status != 0 else ""
         rc = lib.vb200_chol_finish(gram_ptr, cols, _cabi.ptr(params), ctypes.byref(self.info))
+        if status != 0:
+            rc = status
         _remember(self.info)
         # a non-positive pivot is only recorded on the rank that owns its panel: agree before raising
         if phase_times is not None:  # device time between consecutive marks, summed per phase (ms)
             for (_, before), (phase, after) in zip(marks, marks[1:]):
                 phase_times[phase] = phase_times.get(phase, 0.0) + before.elapsed_time(after)
         lowest, highest = dist.agree_on_status(rc)
-        _cabi.check(rc if rc != 0 else (lowest if lowest < 0 else highest), "chol_finish")
+        if rc == 0 and (lowest < 0 or highest > 0):
+            other = lowest if lowest < 0 else highest
+            if other > 0:
+                raise np.linalg.LinAlgError(
+                    "chol_finish: the damped normal matrix is not positive definite (pivot {}, found by another rank)".format(other))
+            raise _cabi.EngineError("chol_finish: another rank failed with status {}".format(other))
+        if status != 0:
+            _cabi.raise_status(rc, "distributed Cholesky", message)
+        _cabi.check(rc, "chol_finish")
         return params
+
+    def backward_error(self, kind, east, north, data, weights, force_east, force_north, mindist, poisson,
+                       force, total_rows, damping):
+        """
+        Normwise backward error of *force* for the (row-sharded) system whose statistics this object holds:
+        every rank evaluates ``J^T W (d - J force)`` over ITS rows matrix-free (``vb200_normal_residual``), the m
+        partial gradients are summed over ranks, ``vb200_backward_error`` forms the ratio.  Stored in
+        ``info.backward_err`` (and returned); needs ``info.lambda_max`` from the solve.
+        """
+        from . import dist
+
+        e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
+        w = None if weights is None else _cabi.f64(weights)
+        grad = self._torch.empty(self.cols, dtype=self._torch.float64, device=self.gram.device)
+        f = force if hasattr(force, "data_ptr") else _cabi.f64(force)
+        rc = self._lib.vb200_normal_residual(int(kind), _cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size,
+                                             _cabi.ptr(fe), _cabi.ptr(fn), fe.size, float(mindist), float(poisson),
+                                             _cabi.ptr(f), _cabi.ptr(grad))
+        lowest, highest = dist.agree_on_status(rc)
+        _cabi.check(rc if rc != 0 else (lowest if lowest < 0 else highest), "normal_residual")
+        dist.allreduce_sum_(grad)
+        self._torch.cuda.synchronize()
+        eta = ctypes.c_double(-1.0)
+        _cabi.check(self._lib.vb200_backward_error(_cabi.ptr(grad), _cabi.ptr(self.stats), self.cols, int(total_rows),
+                                                   float(damping), _cabi.ptr(f), float(self.info.lambda_max),
+                                                   ctypes.byref(eta)), "backward_error")
+        self.info.backward_err = eta.value
+        _remember(self.info)
+        return eta.value
 
     def factor(self, total_rows, damping):
         "Scale, damp and factor in place (the Gram matrix becomes L); keeps 1/s for later solves."
@@ -380,12 +423,26 @@ def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindi
         rows, cols = e.size, fe.size
     _warn_underdetermined(rows, cols)
     _require_damping(damping)
-    system = GramSystem(cols)
-    system.accumulate(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson)
+    # a rank whose accumulation fails (out of memory, bad input) must not strand the others in the all-reduce
+    system, failure = None, None
+    try:
+        system = GramSystem(cols)
+        system.accumulate(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson)
+    except (MemoryError, ValueError, _cabi.EngineError) as exc:  # noqa: PERF203
+        failure = exc
+    lowest, _ = dist.agree_on_status(-1 if failure is not None else 0)
+    if failure is not None:
+        raise failure
+    if lowest < 0:
+        raise _cabi.EngineError("row-sharded fit: the Gram accumulation failed on another rank")
     system.allreduce()
     if dist.use_distributed_cholesky((cols + 127) // 128, 8):
-        return system.solve_distributed(rows, damping, panel_tiles=8)
-    return system.solve(rows, damping)
+        force = system.solve_distributed(rows, damping, panel_tiles=8)
+    else:
+        force = system.solve(rows, damping)
+    if system.info.lambda_max > 0:  # diagnostics on: backward error of the sharded system
+        system.backward_error(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson, force, rows, damping)
+    return force
 
 
 def predict_sharded(east, north, force_east, force_north, mindist, forces, poisson=None):

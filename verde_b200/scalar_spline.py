@@ -294,6 +294,9 @@ class SplineCV(BaseGridder):
         jobs = [(f, i) for f in range(len(folds)) for i in range(len(mindists))]
         sweep = {"jobs": 0, "gram_ms": 0.0, "factor_ms": 0.0, "solve_ms": 0.0, "gemm_ms": 0.0, "gemm_flops": 0.0,
                  "score_s": 0.0}
+        # A failure on one rank (a non-positive-definite system, out of memory) must not strand the others in the
+        # all-reduce of the score table: the rank stops working, still joins the collective, and every rank raises.
+        failure = None
         for job in dist.round_robin(len(jobs)):
             fold, imd = jobs[job]
             train_index, test_index = folds[fold]
@@ -306,11 +309,16 @@ class SplineCV(BaseGridder):
                 force_coords = n_1d_arrays(self.force_coords, n=2)
             train_w = None if train[2][0] is None else train[2][0]
             kernels._warn_underdetermined(east.size, force_coords[0].size)
-            system = kernels.GramSystem(force_coords[0].size)
-            system.accumulate(0, east, north, train[1][0], train_w, force_coords[0], force_coords[1],
-                              mindists[imd])
-            # all dampings of this (fold, mindist) are factored and solved side by side on the device
-            forces = system.solve_multi(east.size, dampings)
+            try:
+                system = kernels.GramSystem(force_coords[0].size)
+                system.accumulate(0, east, north, train[1][0], train_w, force_coords[0], force_coords[1],
+                                  mindists[imd])
+                # all dampings of this (fold, mindist) are factored and solved side by side on the device
+                forces = system.solve_multi(east.size, dampings)
+            except (np.linalg.LinAlgError, MemoryError, kernels._cabi.EngineError) as exc:
+                failure = exc
+                table[imd, :, fold] = np.nan
+                break
             for key in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms", "gemm_flops"):
                 sweep[key] += getattr(system.info, key)
             t0 = time.perf_counter()
@@ -322,6 +330,11 @@ class SplineCV(BaseGridder):
             del system
         self.sweep_info_ = sweep
         table = dist.allreduce_sum_numpy(table)
+        lowest, _ = dist.agree_on_status(-1 if failure is not None else 0)
+        if failure is not None:
+            raise failure
+        if lowest < 0:
+            raise np.linalg.LinAlgError("SplineCV: a (fold, mindist) job failed on another rank")
         scores = table.mean(axis=2).reshape(-1)
         best = int(np.argmax(scores))
         self.spline_ = Spline(mindist=None, damping=combos[best][1], force_coords=self.force_coords,
