@@ -10,10 +10,15 @@ input: ``Spline(damping=1e-6, mindist=1e-5).fit`` followed by the grid predict.
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
   N = 1   50 000 scattered points, forces at the data (50k x 50k FP64 normal
           matrix + Cholesky on one B200), grid 2000 x 2000.
-  N > 1   weak scaling of the same step: 50 000 * N data rows (sharded across
-          ranks, one NCCL all-reduce of the Gram matrix), 50 000 forces from a
-          second seeded scatter, grid 2000 x (2000 * N) points sharded across
-          ranks (at N = 8 this is configs[2]'s 400k x 50k system).
+  N > 1   weak scaling towards BASELINE configs[2]: the first 50 000 * N points of
+          config 3's 400 000-point CheckerBoard scatter (rows sharded across ranks,
+          one NCCL all-reduce of the Gram matrix), weights RandomState(1).uniform(0.1, 10),
+          forces at the 50 151 BlockReduce(np.mean, shape=(224, 224)) block centres of
+          the 400 000 points (computed on the device), grid 2000 x (2000 * N) points
+          sharded across ranks.  N = 8 is configs[2]'s own 400k x 50k system.
+          Outside the timed region every rank also runs the sharded estimator API
+          (Spline, VectorSpline2D, SplineCV) on the reference's golden cases and rank 0
+          reports the gaps in "parity".
 
 Metric: grid points predicted per second of whole-step time (fit + predict),
 whole job.  The JSON line also carries the two quantities BASELINE.json names
@@ -74,11 +79,19 @@ REGION = (0, 5000, -5000, 0)
 # synthetic workload (CheckerBoard defaults of verde/synthetic.py:65-118, scatter of
 # verde/coordinates.py:183-186: easting then northing from RandomState(seed).uniform)
 # ---------------------------------------------------------------------------------------
+CONFIG3_POINTS, CONFIG3_BLOCKS = 400_000, (224, 224)
+
+
+def checkerboard(east, north):
+    return 1000.0 * np.sin((2 * np.pi / 2500.0) * east) * np.cos((2 * np.pi / 2500.0) * north)
+
+
 def make_workload(n_data, n_forces, grid_shape, forces_at_data):
+    "configs[1]-style workload: scatter(size=n_data, random_state=0); separate forces from a second scatter."
     rng = np.random.RandomState(0)
     east = rng.uniform(REGION[0], REGION[1], n_data)
     north = rng.uniform(REGION[2], REGION[3], n_data)
-    data = 1000.0 * np.sin((2 * np.pi / 2500.0) * east) * np.cos((2 * np.pi / 2500.0) * north)
+    data = checkerboard(east, north)
     if forces_at_data:
         fe, fn = east, north
     else:
@@ -87,7 +100,29 @@ def make_workload(n_data, n_forces, grid_shape, forces_at_data):
         fn = rng1.uniform(REGION[2], REGION[3], n_forces)
     ge = np.linspace(east.min(), east.max(), grid_shape[1])
     gn = np.linspace(north.min(), north.max(), grid_shape[0])
-    return east, north, data, fe, fn, ge, gn
+    return east, north, data, None, fe, fn, ge, gn
+
+
+def config3_points():
+    "BASELINE configs[2]'s data: CheckerBoard().scatter(size=400_000, random_state=0) and its weights."
+    rng = np.random.RandomState(0)
+    east = rng.uniform(REGION[0], REGION[1], CONFIG3_POINTS)
+    north = rng.uniform(REGION[2], REGION[3], CONFIG3_POINTS)
+    weights = np.random.RandomState(1).uniform(0.1, 10, CONFIG3_POINTS)
+    return east, north, checkerboard(east, north), weights
+
+
+def make_config3_workload(n_data, grid_shape, block_reduce):
+    """
+    The first *n_data* points of config 3's scatter (all 400 000 at N = 8) with the config's weights; forces at the
+    block centres of ALL 400 000 points -- *block_reduce* is the device BlockReduce on the GPU arm and the numpy
+    block oracle on the CPU arm (they agree: tests/test_gpu_blocks.py::test_config3_force_positions).
+    """
+    east, north, data, weights = config3_points()
+    fe, fn = block_reduce(east, north, data)
+    ge = np.linspace(east.min(), east.max(), grid_shape[1])
+    gn = np.linspace(north.min(), north.max(), grid_shape[0])
+    return east[:n_data], north[:n_data], data[:n_data], weights[:n_data], fe, fn, ge, gn
 
 
 class ClockSampler:
@@ -149,7 +184,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy/C restatement of the reference) on a bounded sample
 # ---------------------------------------------------------------------------------------
-def cpu_reference_step(sample_n, sample_grid, full):
+def cpu_reference_step(sample_n, sample_grid, full, weighted=False):
     """
     Time the reference's CPU algorithm (oracle/ restatement: OpenMP Green's kernels +
     numpy/scipy normal equations, the same BLAS/LAPACK calls sklearn makes) on a
@@ -161,7 +196,7 @@ def cpu_reference_step(sample_n, sample_grid, full):
     import scipy.linalg
     import verde_oracle as vo
 
-    east, north, data, _, _, _, _ = make_workload(sample_n, sample_n, (8, 8), True)
+    east, north, data, _, _, _, _, _ = make_workload(sample_n, sample_n, (8, 8), True)
     t0 = time.perf_counter()
     jac = vo.jacobian(east, north, east, north, MINDIST)
     t_jac = time.perf_counter() - t0
@@ -170,6 +205,10 @@ def cpu_reference_step(sample_n, sample_grid, full):
     jac /= scale
     t_scale = time.perf_counter() - t0
     t0 = time.perf_counter()
+    if weighted:  # sklearn/linear_model/_base.py:223-278: rows of X and y rescaled by sqrt(w) (one more pass over J)
+        sw = np.sqrt(np.random.RandomState(1).uniform(0.1, 10, sample_n))
+        jac *= sw[:, None]
+        data = data * sw
     gram = jac.T @ jac
     rhs = jac.T @ data
     t_gram = time.perf_counter() - t0
@@ -233,19 +272,28 @@ def reference_sample_plan(args):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n = 50_000 * world
-    m = 50_000
-    npts = 2000 * 2000 * world
+    n = args.size * world
+    npts = args.grid * args.grid * world
     cores, pools = force_cpu_threads()
+    weighted = world > 1
+    if world > 1:
+        # the same force positions the GPU arm uses: block centres of config 3's 400 000 points (numpy block oracle)
+        import block_oracle as bo
+
+        ce, cn, _, _ = config3_points()
+        _, labels = bo.block_split((ce, cn), shape=CONFIG3_BLOCKS)
+        m = int(np.unique(labels).size)
+    else:
+        m = args.forces if args.forces else n
     sample_n, sample_grid = args.cpu_sample, 150
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_step(min(1500, sample_n), 40, (n, m, npts))
+        cpu_reference_step(min(1500, sample_n), 40, (n, m, npts), weighted)
     at_least, at_most, budget = reference_sample_plan(args)
     times, samples = [], []
     t_begin = time.perf_counter()
     while len(samples) < at_most:
         t0 = time.perf_counter()
-        samples.append(cpu_reference_step(sample_n, sample_grid, (n, m, npts)))
+        samples.append(cpu_reference_step(sample_n, sample_grid, (n, m, npts), weighted))
         times.append(time.perf_counter() - t0)
         if len(samples) >= at_least and (time.perf_counter() - t_begin) + times[-1] > budget:
             break
@@ -260,7 +308,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": mid["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (mid["fit_s_extrapolated"] + mid["predict_s_extrapolated"]),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world),
+        "config": workload_config(world, args.size, m, args.grid),
         "fit_s": mid["fit_s_extrapolated"], "predict_gpts_per_s": npts / mid["predict_s_extrapolated"] * 1e-9,
         "cpu_baseline": {"value": mid["value"], "unit": UNIT, "cores": cores, "threads": pools, "kind": "port",
                          "sample": sample, "samples_timed": len(samples), "sample_wall_s": statistics.median(times),
@@ -273,20 +321,120 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(world, n_rank=50_000, m=50_000, grid=2000):
+    if world > 1:
+        full = (n_rank * world, grid) == (CONFIG3_POINTS, 2000)
+        return {
+            "workload": ("{}: Spline(damping=1e-6, mindist=1e-5), the first {} of config 3's 400000 CheckerBoard points "
+                         "(rows sharded over {} ranks), weights RandomState(1).uniform(0.1, 10), {} forces at the "
+                         "BlockReduce(mean, shape=(224, 224)) centres of the 400000 points, grid {}x{} sharded".format(
+                             "BASELINE configs[2]'s 400k x 50k system" if full else "weak-scaled towards BASELINE configs[2]",
+                             n_rank * world, world, m, grid, grid * world)),
+            "n_data": n_rank * world, "n_forces": m, "grid_points": grid * grid * world, "weights": True,
+            "damping": DAMPING, "mindist": MINDIST, "parallelism": "rows+grid sharded x{}".format(world),
+            "l2": "inputs larger than L2 (10 GB Gram matrix streamed); no explicit flush",
+        }
     base = "BASELINE configs[1]" if (n_rank, m, grid) == (50_000, 50_000, 2000) else "REDUCED-SIZE variant of configs[1]"
-    if world == 1 and m != n_rank:
+    if m != n_rank:
         base = ("BASELINE configs[2] on one GPU" if (n_rank, m, grid) == (400_000, 50_000, 10_000)
                 else "configs[2]-style system (separate forces)")
     return {
-        "workload": ("{}: Spline(damping=1e-6, mindist=1e-5), CheckerBoard scatter of {} points, "
-                     "{}, grid {}x{}".format(base, n_rank, "forces at data" if m == n_rank else "{} separate forces".format(m),
-                                             grid, grid) if world == 1 else
-                     "weak-scaled {} (= configs[2] at N=8 and full size): {} data rows sharded over {} ranks, {} forces, "
-                     "grid {}x{} sharded".format(base, n_rank * world, world, m, grid, grid * world)),
-        "n_data": n_rank * world, "n_forces": m, "grid_points": grid * grid * world,
-        "damping": DAMPING, "mindist": MINDIST, "parallelism": "rows+grid sharded x{}".format(world),
+        "workload": "{}: Spline(damping=1e-6, mindist=1e-5), CheckerBoard scatter of {} points, {}, grid {}x{}".format(
+            base, n_rank, "forces at data" if m == n_rank else "{} separate forces".format(m), grid, grid),
+        "n_data": n_rank, "n_forces": m, "grid_points": grid * grid, "weights": False,
+        "damping": DAMPING, "mindist": MINDIST, "parallelism": "rows+grid sharded x1",
         "l2": "inputs larger than L2 (10 GB Gram matrix streamed); no explicit flush",
     }
+
+
+# ---------------------------------------------------------------------------------------
+# N > 1: the sharded estimator API against the reference's golden vectors (outside the timed region)
+# ---------------------------------------------------------------------------------------
+def multi_gpu_parity(vb, world):
+    """
+    Every rank runs the SAME estimator calls a user would (torch.distributed initialised -> Spline/VectorSpline2D
+    fits are row-sharded with one Gram all-reduce and the panel-cyclic Cholesky where it applies, predicts are
+    point-sharded, SplineCV deals its (fold, mindist) jobs round-robin) and compares with tests/golden/*.npz,
+    which were produced by the UNMODIFIED reference (oracle/make_golden*.py).  Collective: all ranks must call it.
+    """
+    golden = os.path.join(ROOT, "tests", "golden")
+    eps = np.finfo(np.float64).eps
+    out = {"world": world, "against": "golden vectors of the unmodified reference (tests/golden)"}
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # small goldens: n = 240 weighted Spline, 150-station VectorSpline2D, SplineCV 4 x 3 x 5 on 300 points
+        g = np.load(os.path.join(golden, "spline_small.npz"))
+        e, n, d, w = g["east"], g["north"], g["data"], g["weights"]
+        sp = vb.Spline(damping=1e-4).fit((e, n), d, weights=w)
+        out["spline_small_force"] = rel(sp.force_, g["force_d1em4_w"])
+        out["spline_small_grid"] = float(np.max(np.abs(sp.predict((g["grid_east"], g["grid_north"])) - g["grid_d1em4_w"])) / np.ptp(d))
+        vb.dist.set_sharding(False)
+        single = vb.Spline(damping=1e-4).fit((e, n), d, weights=w)
+        vb.dist.set_sharding("auto")
+        out["sharded_vs_single_force"] = rel(sp.force_, single.force_)
+        vb.dist.set_cholesky("distributed")  # tiny system: panel-cyclic factorisation forced on
+        spd = vb.Spline(damping=1e-4).fit((e, n), d, weights=w)
+        vb.dist.set_cholesky("auto")
+        out["distributed_vs_replicated_cholesky_force"] = rel(spd.force_, sp.force_)
+        v = np.load(os.path.join(golden, "vector_small.npz"))
+        vs = vb.VectorSpline2D(damping=1e-3).fit((v["east"], v["north"]), (v["data_east"], v["data_north"]))
+        out["vector_small_force"] = rel(vs.force_, v["force_d1em3"])
+        c = np.load(os.path.join(golden, "splinecv_small.npz"))
+        cv = vb.SplineCV(dampings=list(c["dampings"]), mindists=list(c["mindists"])).fit((c["east"], c["north"]), c["data"])
+        out["cv_small_scores"] = float(np.max(np.abs(cv.scores_ - c["scores"])))
+        out["cv_small_best_matches"] = bool((cv.mindist_, cv.damping_) == (float(c["best_mindist"]), float(c["best_damping"])))
+
+        # config-3 shape: 40 000 rows sharded x 5 041 BlockReduce-centre forces, weighted (cond 1.9e11 twin)
+        g3 = np.load(os.path.join(golden, "cfg3_40k.npz"))
+        tab = vb.CheckerBoard().scatter(size=40_000, random_state=0)
+        e, n, d = tab.easting.values, tab.northing.values, tab.scalars.values
+        w = np.random.RandomState(1).uniform(0.1, 10, e.size)
+        fc = (g3["force_east"], g3["force_north"])
+        full = vb.grid_coordinates((e.min(), e.max(), n.min(), n.max()), shape=(600, 600))
+        sub = (full[0][::8, ::8], full[1][::8, ::8])
+        sp = vb.Spline(damping=1e-2, mindist=1e-5, force_coords=fc).fit((e, n), d, weights=w)
+        cond = float(g3["cond_d1em2"])
+        out["cfg3_40k"] = {"cond": cond, "force": rel(sp.force_, g3["force_d1em2"]),
+                           "grid_over_range": float(np.max(np.abs(sp.predict(sub) - g3["grid_sub_d1em2"])) / np.ptp(d)),
+                           "force_tol": max(1e-9, 10 * cond * eps), "cond_est": sp.fit_info_.get("cond_est"),
+                           "backward_err": sp.fit_info_.get("backward_err")}
+
+        # config-4 shape: VectorSpline2D on 3 000 stations (6 000 x 6 000), row-sharded, panel-cyclic Cholesky
+        g4 = np.load(os.path.join(golden, "cfg4_3k.npz"))
+        region = (0, 500e3, 0, 500e3)
+        se, sn = vb.scatter_points(region, 3000, random_state=0)
+        ue = 10 * np.sin(2 * np.pi * se / 3e5) * np.cos(2 * np.pi * sn / 4.5e5) + 3
+        un = -7 * np.cos(2 * np.pi * se / 4.5e5) * np.sin(2 * np.pi * sn / 3e5) + 1
+        vs = vb.VectorSpline2D(poisson=0.5, mindist=10e3, damping=1e-3).fit((se, sn), (ue, un))
+        full = vb.grid_coordinates(region, shape=(200, 200))
+        ge, gn = vs.predict((full[0][::5, ::5], full[1][::5, ::5]))
+        cond = float(g4["cond_d1em3"])
+        out["cfg4_3k"] = {"cond": cond, "force": rel(vs.force_, g4["force_d1em3"]),
+                          "grid_over_range": max(float(np.max(np.abs(ge - g4["grid_east_sub_d1em3"])) / np.ptp(ue)),
+                                                 float(np.max(np.abs(gn - g4["grid_north_sub_d1em3"])) / np.ptp(un))),
+                          "force_tol": max(1e-9, 10 * cond * eps), "cond_est": vs.fit_info_.get("cond_est"),
+                          "backward_err": vs.fit_info_.get("backward_err")}
+
+        # config-5 shape: SplineCV 6 dampings x 4 mindists x 5 folds on 2 000 points, 20 Gram jobs dealt to the ranks
+        g5 = np.load(os.path.join(golden, "cfg5_2k.npz"))
+        tab = vb.CheckerBoard().scatter(size=2000, random_state=0)
+        e, n, d = tab.easting.values, tab.northing.values, tab.scalars.values
+        cv = vb.SplineCV(dampings=list(g5["dampings"]), mindists=list(g5["mindists"])).fit((e, n), d)
+        diff = np.abs(cv.scores_ - g5["scores"]).reshape(len(g5["mindists"]), len(g5["dampings"]))
+        out["cfg5_2k"] = {"scores_max_diff_by_damping": {str(float(x)): float(diff[:, k].max()) for k, x in enumerate(g5["dampings"])},
+                          "best_matches": bool((cv.mindist_, cv.damping_) == (float(g5["best_mindist"]), float(g5["best_damping"]))),
+                          "jobs_this_rank": int(cv.sweep_info_["jobs"])}
+    ok = (out["spline_small_force"] < 1e-5 and out["spline_small_grid"] < 1e-6 and out["vector_small_force"] < 1e-6
+          and out["distributed_vs_replicated_cholesky_force"] < 1e-9 and out["cv_small_scores"] < 1e-7
+          and out["cv_small_best_matches"] and out["cfg3_40k"]["force"] <= out["cfg3_40k"]["force_tol"]
+          and out["cfg3_40k"]["grid_over_range"] < 1e-6 and out["cfg4_3k"]["force"] <= out["cfg4_3k"]["force_tol"]
+          and out["cfg4_3k"]["grid_over_range"] < 1e-6 and out["cfg5_2k"]["best_matches"]
+          and max(v for k, v in out["cfg5_2k"]["scores_max_diff_by_damping"].items() if float(k) >= 1e-4) < 1e-7)
+    out["ok"] = bool(ok)
+    return out
 
 
 # ---------------------------------------------------------------------------------------
@@ -308,6 +456,8 @@ def main():
                     help="--impl reference: wall-clock seconds after which no further sample is started")
     ap.add_argument("--cholesky", default="auto", choices=["auto", "replicated", "distributed"],
                     help="N > 1: replicated m x m Cholesky on every rank, or panel-cyclic over the ranks")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the end-to-end arm (at most --steps)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-estimator parity block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -342,12 +492,24 @@ def main():
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n_rank = args.size
-    m = args.forces if args.forces else (args.size if world == 1 else min(50_000, args.size))
     n_total = n_rank * world
-    forces_at_data = world == 1 and m == n_total and not args.forces
     grid_shape = (args.grid, args.grid * world)
     npts_total = grid_shape[0] * grid_shape[1]
-    east, north, data, fe, fn, ge, gn = make_workload(n_total, m, grid_shape, forces_at_data=forces_at_data)
+    if world > 1:
+        def device_block_centres(ce, cn, cd):
+            "force positions of config 3: BlockReduce on the device (vb_block.cu), as the config takes them"
+            (be, bn), _ = vb.BlockReduce(np.mean, shape=CONFIG3_BLOCKS, center_coordinates=True).filter((ce, cn), cd)
+            return be, bn
+
+        vb.dist.set_sharding(False)  # the block reduction of the 400 000 points is replicated setup work
+        east, north, data, weights, fe, fn, ge, gn = make_config3_workload(n_total, grid_shape, device_block_centres)
+        vb.dist.set_sharding("auto")
+        m = int(fe.size)
+        forces_at_data = False
+    else:
+        m = args.forces if args.forces else args.size
+        forces_at_data = m == n_total and not args.forces
+        east, north, data, weights, fe, fn, ge, gn = make_workload(n_total, m, grid_shape, forces_at_data=forces_at_data)
     gx, gy = np.meshgrid(ge, gn)
     gx, gy = gx.ravel(), gy.ravel()
     a, b = vb.dist.shard_bounds(n_total, rank, world)
@@ -355,9 +517,10 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     def to_dev(x):
-        return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        return None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev)
 
     d_e, d_n, d_d = to_dev(east[a:b]), to_dev(north[a:b]), to_dev(data[a:b])
+    d_w = to_dev(None if weights is None else weights[a:b])
     d_fe, d_fn = to_dev(fe), to_dev(fn)
     d_gx, d_gy = to_dev(gx[pa:pb]), to_dev(gy[pa:pb])
     d_force = torch.empty(m, dtype=torch.float64, device=dev)
@@ -384,7 +547,7 @@ def main():
             _cabi.check(rc, "bench fit")
         else:
             ctypes.memset(ctypes.byref(info), 0, ctypes.sizeof(info))
-            rc = lib.vb200_gram_accumulate(0, _cabi.ptr(d_e), _cabi.ptr(d_n), _cabi.ptr(d_d), None, b - a,
+            rc = lib.vb200_gram_accumulate(0, _cabi.ptr(d_e), _cabi.ptr(d_n), _cabi.ptr(d_d), _cabi.ptr(d_w), b - a,
                                            _cabi.ptr(d_fe), _cabi.ptr(d_fn), m, MINDIST, 0.0,
                                            _cabi.ptr(system.gram), _cabi.ptr(system.stats), 0, ctypes.byref(info))
             _cabi.check(rc, "bench gram")
@@ -396,6 +559,9 @@ def main():
                 rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, DAMPING, 0,
                                           _cabi.ptr(d_force), ctypes.byref(info))
                 _cabi.check(rc, "bench solve")
+                system.info = info
+            if info.lambda_max > 0:  # diagnostics on: backward error of the row-sharded system (m doubles all-reduced)
+                system.backward_error(0, d_e, d_n, d_d, d_w, d_fe, d_fn, MINDIST, 0.0, d_force, n_total, DAMPING)
         ev[1].record()
         rc = lib.vb200_predict(_cabi.ptr(d_gx), _cabi.ptr(d_gy), pb - pa, _cabi.ptr(d_fe), _cabi.ptr(d_fn),
                                _cabi.ptr(d_force), m, MINDIST, _cabi.ptr(d_out))
@@ -452,6 +618,7 @@ def main():
             return t.numpy()
 
         h_e, h_n, h_d = pinned(east), pinned(north), pinned(data)
+        h_w = None if weights is None else pinned(weights)
         h_gx, h_gy = pinned(gx), pinned(gy)
         force_coords = None if forces_at_data else (pinned(fe), pinned(fn))
         result = {}
@@ -460,22 +627,26 @@ def main():
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore", FutureWarning)
                 spline = vb.Spline(damping=DAMPING, mindist=MINDIST, force_coords=force_coords)
-            spline.fit((h_e, h_n), h_d)
+            spline.fit((h_e, h_n), h_d, weights=h_w)
             result["grid"] = spline.predict((h_gx, h_gy))
             result["force"] = spline.force_
 
         for _ in range(max(1, min(args.warmup, 1))):
             api_step()
-        e2e_steps = max(1, min(args.steps, 2))
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
         e2e_ms = timed(api_step, e2e_steps) / e2e_steps
-        h2d = 8 * ((b - a) * 3 + (0 if forces_at_data else 2 * m) + 2 * m + 2 * (pb - pa) + m)
+        h2d = 8 * ((b - a) * (3 if weights is None else 4) + (0 if forces_at_data else 2 * m) + 2 * m + 2 * (pb - pa) + m)
         d2h = 8 * (m + (pb - pa))
-        e2e = {"value": npts_total / (e2e_ms * 1e-3) * 1e-6, "unit": UNIT, "ms_per_step": e2e_ms,
+        e2e = {"value": npts_total / (e2e_ms * 1e-3) * 1e-6, "unit": UNIT, "ms_per_step": e2e_ms, "e2e_steps": e2e_steps,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "verde_b200.Spline.fit + Spline.predict (host numpy, pinned)"}
         # parity spot check of the two arms against each other (same forces, same grid)
         dev_force = d_force.cpu().numpy()
         e2e["force_vs_device_arm"] = float(np.max(np.abs(result["force"] - dev_force)) / np.max(np.abs(dev_force)))
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(vb, world)
 
     if rank != 0:
         if world > 1:
@@ -516,7 +687,15 @@ def main():
         },
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "diag_min_max": [phase["info"]["diag_min"], phase["info"]["diag_max"]],
+        # SURVEY 8b out_diag{cond, backward_err}: computed inside every timed step (vb_diag.cu)
+        "conditioning": {"cond_est": phase["info"]["cond_est"], "cond_upper": phase["info"]["cond_upper"],
+                         "lambda_max": phase["info"]["lambda_max"], "lambda_min_est": phase["info"]["lambda_min_est"],
+                         "backward_err": phase["info"]["backward_err"], "diag_ms_per_step": phase["info"]["diag_ms"],
+                         "note": "A = D G D + damping I (the matrix the reference's Ridge factors); cond_est <= cond_2(A) <= "
+                                 "cond_upper; backward_err = ||Js^T W (d - Js c) - damping c|| / (lambda_max ||c|| + ||Js^T W d||)"},
     }
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_cpu_baseline and world == 1:
         cores, pools = force_cpu_threads()
         cpu = cpu_reference_step(args.cpu_sample, 150, (n_total, m, npts_total))

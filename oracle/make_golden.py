@@ -194,6 +194,7 @@ def main():
         out["force_" + tag] = sp.force_
         out["grid_sub_" + tag] = sp.predict(sub)
         out["pred_data_" + tag] = sp.predict((e[:500], n[:500]))
+        out["cond_" + tag] = cond_estimate(vd, sp.jacobian((e, n), (e, n)), None, damping)
     np.savez_compressed(os.path.join(GOLDEN, "cfg1_5k.npz"), **out, **ver)
     for name in sorted(os.listdir(GOLDEN)):
         print(name, os.path.getsize(os.path.join(GOLDEN, name)))

@@ -51,9 +51,50 @@ def test_workload_generator_matches_checkerboard():
     import bench
     import verde_b200 as vb
 
-    east, north, data, fe, fn, ge, gn = bench.make_workload(3000, 3000, (10, 12), True)
+    east, north, data, weights, fe, fn, ge, gn = bench.make_workload(3000, 3000, (10, 12), True)
+    assert weights is None
     tab = vb.CheckerBoard().scatter(size=3000, random_state=0)
     np.testing.assert_array_equal(east, tab.easting.values)
     np.testing.assert_array_equal(north, tab.northing.values)
     np.testing.assert_allclose(data, tab.scalars.values, rtol=1e-13, atol=1e-10)
     assert fe is east and ge.size == 12 and gn.size == 10
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_environment():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must still use every host core, on rank 0 of
+    a 2-rank launch, on config 3's weak-scaled workload (weights, BlockReduce-centre forces), and say so."""
+    import bench
+
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "1",
+           "--cpu-sample", "1000", "--cpu-budget", "1"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = json.loads(proc.stdout.strip())
+    cpu = line["cpu_baseline"]
+    assert cpu["cores"] == bench.host_cores()
+    assert cpu["threads"] and all(v == cpu["cores"] for v in cpu["threads"].values()), cpu["threads"]
+    assert cpu["samples_timed"] == 3 and "median of 3 samples" in cpu["sample"]
+    assert cpu["values_min_max"][0] <= line["value"] <= cpu["values_min_max"][1]
+    cfg = line["config"]
+    assert line["n_gpus"] == 2 and cfg["n_data"] == 100_000 and cfg["n_forces"] == 50_151 and cfg["weights"] is True
+    assert cfg["grid_points"] == 8_000_000
+
+
+def test_config3_workload_generator():
+    import numpy as np
+
+    import bench
+
+    calls = []
+
+    def fake_reduce(e, n, d):
+        calls.append(e.size)
+        return e[:7], n[:7]
+
+    east, north, data, weights, fe, fn, ge, gn = bench.make_config3_workload(1000, (4, 8), fake_reduce)
+    assert calls == [400_000] and east.size == north.size == data.size == weights.size == 1000 and fe.size == 7
+    rng = np.random.RandomState(0)
+    np.testing.assert_array_equal(east, rng.uniform(0, 5000, 400_000)[:1000])
+    np.testing.assert_array_equal(weights, np.random.RandomState(1).uniform(0.1, 10, 400_000)[:1000])
+    assert ge.size == 8 and gn.size == 4

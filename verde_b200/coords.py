@@ -1,3 +1,8 @@
+# Host glue derived from fatiando/verde (BSD 3-Clause): it restates the reference's estimator contract, error and
+# warning texts so that this path is a drop-in.
+#   Copyright (c) 2017 The Verde Developers.  Distributed under the terms of the BSD 3-Clause License.
+#   SPDX-License-Identifier: BSD-3-Clause
+#   This code is part of the Fatiando a Terra project (https://www.fatiando.org); see LICENSE-verde.txt.
 """
 Coordinate generators that define the input / grid layout of the spline path.
 

@@ -342,13 +342,17 @@ class GramSystem:
         """
         from . import dist
 
-        e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
-        w = None if weights is None else _cabi.f64(weights)
+        def as_input(a):  # host arrays are made contiguous float64; CUDA tensors pass through as device pointers
+            return a if hasattr(a, "data_ptr") else _cabi.f64(a)
+
+        e, n, d, fe, fn, f = (as_input(a) for a in (east, north, data, force_east, force_north, force))
+        w = None if weights is None else as_input(weights)
         grad = self._torch.empty(self.cols, dtype=self._torch.float64, device=self.gram.device)
-        f = force if hasattr(force, "data_ptr") else _cabi.f64(force)
-        rc = self._lib.vb200_normal_residual(int(kind), _cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size,
-                                             _cabi.ptr(fe), _cabi.ptr(fn), fe.size, float(mindist), float(poisson),
-                                             _cabi.ptr(f), _cabi.ptr(grad))
+        rc = self._lib.vb200_normal_residual(int(kind), _cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w),
+                                             int(e.numel() if hasattr(e, "numel") else e.size),
+                                             _cabi.ptr(fe), _cabi.ptr(fn),
+                                             int(fe.numel() if hasattr(fe, "numel") else fe.size), float(mindist),
+                                             float(poisson), _cabi.ptr(f), _cabi.ptr(grad))
         lowest, highest = dist.agree_on_status(rc)
         _cabi.check(rc if rc != 0 else (lowest if lowest < 0 else highest), "normal_residual")
         dist.allreduce_sum_(grad)
