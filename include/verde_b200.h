@@ -36,6 +36,7 @@ extern "C" {
 #define VB200_E_BADARG (-1)
 #define VB200_E_CUDA (-2)
 #define VB200_E_NOMEM (-3)
+#define VB200_E_NOCONV (-4) /* the Jacobi SVD of a *_lstsq call did not converge within its sweep limit */
 
 /* Diagnostics of one fit (all optional; pass NULL to skip). */
 typedef struct vb200_fit_info {
@@ -61,6 +62,11 @@ typedef struct vb200_fit_info {
                                 Green's functions; only the fused fits (vb200_spline_fit*, vb200_least_squares) and
                                 vb200_backward_error fill it, otherwise -1                       */
     double diag_ms;          /* device + host time spent on these diagnostics                   */
+    /* --- the damping=None entry points (vb200_*_lstsq) only; 0 otherwise --- */
+    int64_t svd_rank;        /* singular values kept: sigma > rcond * sigma_max (LinearRegression.rank_) */
+    int64_t svd_sweeps;      /* one-sided Jacobi sweeps until a sweep without rotations        */
+    double sigma_max;        /* largest / smallest KEPT singular value of sqrt(W) Js           */
+    double sigma_min_kept;
 } vb200_fit_info;
 
 /* ---- library / device -------------------------------------------------------------- */
@@ -198,6 +204,26 @@ int vb200_chol_solve(const double *chol_dev, const double *inv_scale_dev, int64_
 int vb200_jacobian_transpose_apply(const double *east, const double *north, int64_t n,
                                    const double *force_east, const double *force_north, int64_t m,
                                    double mindist, const double *v, double *out);
+
+/* ---- damping=None ------------------------------------------------------------
+ * replaces verde/base/least_squares.py:65-70 with damping=None: StandardScaler column scaling, then
+ * LinearRegression(fit_intercept=False).fit(Js, d, sample_weight=w) = scipy.linalg.lstsq(sqrt(W) Js, sqrt(W) d,
+ * cond=rcond) -- the minimum-norm solution with every singular value <= rcond * sigma_max dropped (LAPACK gelsd) --
+ * unscaled on return.  rcond is the caller's: scikit-learn 1.9 passes LinearRegression.tol = 1e-6.  Computed by a
+ * one-sided Jacobi SVD of the explicit scaled Jacobian on the device (vb_svd.cu); arguments otherwise as the damped
+ * twins above.  info (optional) receives svd_rank, svd_sweeps, sigma_max, sigma_min_kept, cond_est =
+ * sigma_max / sigma_min_kept and solve_ms.  Returns VB200_E_NOCONV if the sweeps do not converge. */
+int vb200_spline_fit_lstsq(const double *east, const double *north, const double *data,
+                           const double *weights, int64_t n, const double *force_east,
+                           const double *force_north, int64_t m, double mindist, double rcond,
+                           double *out_force, vb200_fit_info *info);
+int vb200_spline_fit_2d_lstsq(const double *east, const double *north, const double *data,
+                              const double *weights, int64_t n, const double *force_east,
+                              const double *force_north, int64_t m, double mindist, double poisson,
+                              double rcond, double *out_force, vb200_fit_info *info);
+int vb200_least_squares_lstsq(const double *jac, int64_t n, int64_t m, const double *data,
+                              const double *weights, double rcond, double *out_params,
+                              vb200_fit_info *info);
 
 /* Diagnostics for the staged (multi-GPU) fit, SURVEY 8b out_diag{cond, backward_err}:
  * vb200_normal_residual: grad = J^T W (d - J force) over THIS caller's rows, matrix-free with the exact Green's

@@ -131,8 +131,9 @@ def test_config5_shape_splinecv_6x4x5_on_2000_points(vb):
     diff = np.abs(cv.scores_ - ref)
     # R^2 of a fold's predictions inherits the solve's cond * eps: systems with damping 1e-8 sit at cond ~ 1e15
     # (2000 points), those with damping >= 1e-4 at cond <= 1e11
-    by_damping = {1e-8: 1e-4, 1e-6: 1e-5}
-    tol = np.array([by_damping.get(float(damp), 1e-7) for _ in mindists for damp in dampings])
+    # (observed on B200: 2.1e-8 at damping 1e-8, 1.3e-9 at 1e-6, <= 2.1e-10 from 1e-4 up)
+    by_damping = {1e-8: 1e-6, 1e-6: 1e-7}
+    tol = np.array([by_damping.get(float(damp), 1e-8) for _ in mindists for damp in dampings])
     observed = dict(score_max_diff=float(diff.max()), score_diff_by_damping={
         str(damp): float(diff.reshape(len(mindists), len(dampings))[:, k].max()) for k, damp in enumerate(dampings)},
         best=(float(cv.mindist_), float(cv.damping_)), cond_best=float(g["cond_best"]))

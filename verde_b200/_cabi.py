@@ -17,7 +17,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 i64 = ctypes.c_int64
 dbl = ctypes.c_double
 
-E_BADARG, E_CUDA, E_NOMEM = -1, -2, -3
+E_BADARG, E_CUDA, E_NOMEM, E_NOCONV = -1, -2, -3, -4
 
 
 class FitInfo(ctypes.Structure):
@@ -43,6 +43,10 @@ class FitInfo(ctypes.Structure):
         ("cond_upper", ctypes.c_double),
         ("backward_err", ctypes.c_double),
         ("diag_ms", ctypes.c_double),
+        ("svd_rank", ctypes.c_int64),
+        ("svd_sweeps", ctypes.c_int64),
+        ("sigma_max", ctypes.c_double),
+        ("sigma_min_kept", ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -85,6 +89,9 @@ SIGNATURES = {
     "vb200_gram_factor": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_chol_solve": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [ctypes.POINTER(FitInfo)]),
     "vb200_jacobian_transpose_apply": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl] + [ctypes.c_void_p] * 2),
+    "vb200_spline_fit_lstsq": (ctypes.c_int, [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+    "vb200_spline_fit_2d_lstsq": (ctypes.c_int, [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl, dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
+    "vb200_least_squares_lstsq": (ctypes.c_int, [ctypes.c_void_p, i64, i64] + [ctypes.c_void_p] * 2 + [dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_normal_residual": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 4 + [i64] + [ctypes.c_void_p] * 2 + [i64, dbl, dbl] + [ctypes.c_void_p] * 2),
     "vb200_backward_error": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, i64, dbl, ctypes.c_void_p, dbl, ctypes.POINTER(dbl)]),
     "vb200_least_squares": (ctypes.c_int, [ctypes.c_void_p, i64, i64] + [ctypes.c_void_p] * 2 + [dbl, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),

@@ -50,6 +50,7 @@ struct Options {
     int gram_fused = 0;
     int sweep_group = 0;  // damped systems factored side by side in vb200_gram_solve_multi (0 = as many as fit)
     int fit_diagnostics = 1;  // condition estimate + backward error after every fit (vb_diag.cu)
+    int svd_max_sweeps = 80;  // sweep limit of the damping=None Jacobi SVD (vb_svd.cu)
 } g_opt;
 
 // ---- cached workspace (grow-only, per process; one process per GPU) --------------------
@@ -441,6 +442,7 @@ int vb200_set_option(const char *key, double value)
     else if (k == "gram_fused") g_opt.gram_fused = value != 0.0;
     else if (k == "sweep_group") g_opt.sweep_group = value < 0 ? 0 : (int)value;
     else if (k == "fit_diagnostics") g_opt.fit_diagnostics = value != 0.0;
+    else if (k == "svd_max_sweeps") g_opt.svd_max_sweeps = value < 1 ? 1 : (int)value;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
     else if (k == "predict_minb") vb_predict_minb = (int)value;
@@ -1445,6 +1447,96 @@ int vb200_backward_error(const double *grad, const double *stats_dev, int64_t co
     CU(ws_get("diag_rhs", sizeof(double) * Mpad, (void **)&rhs));
     CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale, rhs, st));
     return backward_error_dev(dgrad, stats_dev, inv_scale, dforce, cols, damping, lambda_max, eta, st);
+}
+
+static int lstsq_impl(int kind, const double *jac, const double *east, const double *north, const double *data,
+                      const double *weights, int64_t n, const double *force_east, const double *force_north,
+                      int64_t m, double mindist, double poisson, double rcond, double *out_force, vb200_fit_info *info)
+{
+    if (info) memset(info, 0, sizeof(*info));
+    if (n <= 0 || m <= 0) return fail(VB200_E_BADARG, "bad sizes n=%lld m=%lld", (long long)n, (long long)m);
+    if (!(rcond >= 0.0) || !(rcond < 1.0)) return fail(VB200_E_BADARG, "rcond must be in [0, 1)");
+    if (!data || !out_force || (kind == 2 ? !jac : (!east || !north || !force_east || !force_north)))
+        return fail(VB200_E_BADARG, "null pointer");
+    cudaStream_t st = 0;
+    VbGramProblem pb;
+    int rc = stage_problem(kind, jac, east, north, data, weights, n, force_east, force_north, m, mindist, poisson, &pb, st);
+    if (rc != 0) return rc;
+    const long long rows = vb_sys_rows(pb), cols = vb_sys_cols(pb);
+    if (cols > 0x3fffffffLL) return fail(VB200_E_BADARG, "too many unknowns");
+    const long long Mpad = vb200_padded_cols(cols), mp = cols + (cols & 1);
+    const long long launches0 = vb_launch_counter;
+    Span whole;
+    CU(span_begin(&whole, st));
+    const double *jdev = pb.jac;
+    if (kind != 2) {
+        double *jbuf;
+        CU(ws_get("svd_jac", sizeof(double) * (size_t)rows * cols, (void **)&jbuf));
+        if (kind == 0) CU(vb_launch_jacobian(pb.east, pb.north, n, pb.fe, pb.fn, m, mindist, jbuf, st));
+        else CU(vb_launch_jacobian2d(pb.east, pb.north, n, pb.fe, pb.fn, m, mindist, poisson, jbuf, st));
+        jdev = jbuf;
+    }
+    double *inv_scale, *stack, *work;
+    unsigned *counter;
+    CU(ws_get("inv_scale", sizeof(double) * Mpad, (void **)&inv_scale));
+    CU(ws_get("svd_stack", sizeof(double) * (size_t)vb_svd_stack_doubles(rows, cols), (void **)&stack));
+    CU(ws_get("svd_work", sizeof(double) * (size_t)(3 * mp + 8), (void **)&work));
+    CU(ws_get("svd_counter", sizeof(unsigned), (void **)&counter));
+    OutBuf ob;
+    CU(stage_out("out_params", out_force, cols, &ob));
+    CU(vb_svd_inv_scale(jdev, rows, cols, Mpad, inv_scale, st));
+    VbSvdResult res = {};
+    CU(vb_svd_solve(jdev, pb.data, pb.weights, inv_scale, rows, cols, rcond, g_opt.svd_max_sweeps, stack, work, counter,
+                    ob.dev, &res, st));
+    CU(cudaEventRecord(whole.b, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    const double ms = span_ms(whole);
+    if (info) {
+        info->block_rows = (int32_t)(Mpad / VB_TILE);
+        info->rows = rows;
+        info->cols = cols;
+        info->solve_ms = ms;
+        info->kernel_launches = vb_launch_counter - launches0;
+        info->svd_rank = res.rank;
+        info->svd_sweeps = res.sweeps;
+        info->sigma_max = res.sigma_max;
+        info->sigma_min_kept = res.sigma_min_kept;
+        info->lambda_max = res.sigma_max * res.sigma_max;
+        info->lambda_min_est = res.sigma_min_kept * res.sigma_min_kept;
+        info->cond_est = res.sigma_min_kept > 0.0 ? res.sigma_max / res.sigma_min_kept : 0.0;
+        info->cond_upper = rcond > 0.0 ? 1.0 / rcond : 0.0;
+        info->backward_err = -1.0;
+    }
+    if (!res.converged)
+        return fail(VB200_E_NOCONV, "one-sided Jacobi SVD did not converge in %d sweeps (%lld x %lld system)", res.sweeps,
+                    rows, cols);
+    return 0;
+}
+
+int vb200_spline_fit_lstsq(const double *east, const double *north, const double *data,
+                           const double *weights, int64_t n, const double *force_east,
+                           const double *force_north, int64_t m, double mindist, double rcond,
+                           double *out_force, vb200_fit_info *info)
+{
+    return lstsq_impl(0, nullptr, east, north, data, weights, n, force_east, force_north, m, mindist, 0.0, rcond,
+                      out_force, info);
+}
+
+int vb200_spline_fit_2d_lstsq(const double *east, const double *north, const double *data,
+                              const double *weights, int64_t n, const double *force_east,
+                              const double *force_north, int64_t m, double mindist, double poisson,
+                              double rcond, double *out_force, vb200_fit_info *info)
+{
+    return lstsq_impl(1, nullptr, east, north, data, weights, n, force_east, force_north, m, mindist, poisson, rcond,
+                      out_force, info);
+}
+
+int vb200_least_squares_lstsq(const double *jac, int64_t n, int64_t m, const double *data,
+                              const double *weights, double rcond, double *out_params,
+                              vb200_fit_info *info)
+{
+    return lstsq_impl(2, jac, nullptr, nullptr, data, weights, n, nullptr, nullptr, m, 0.0, 0.0, rcond, out_params, info);
 }
 
 int vb200_spline_fit(const double *east, const double *north, const double *data,

@@ -152,6 +152,20 @@ cudaError_t vb_launch_backward_norms(const double *grad, const double *jtwd, con
 cudaError_t vb_launch_gemv(const double *jac, long long n, long long m, const double *v, int transpose, double *out,
                            cudaStream_t st);
 
+// ---- damping=None: truncated minimum-norm least squares by one-sided Jacobi SVD (vb_svd.cu) ----------
+struct VbSvdResult {
+    long long rank;       // singular values kept: sigma > rcond * sigma_max
+    double sigma_max, sigma_min_kept;
+    int sweeps, converged;
+    long long rotations;
+};
+long long vb_svd_stack_doubles(long long rows, long long cols);
+cudaError_t vb_svd_inv_scale(const double *jac, long long rows, long long cols, long long Mpad, double *inv_scale,
+                             cudaStream_t st);
+cudaError_t vb_svd_solve(const double *jac, const double *data, const double *weights, const double *inv_scale,
+                         long long rows, long long cols, double rcond, int max_sweeps, double *A, double *work,
+                         unsigned *counter, double *params, VbSvdResult *res, cudaStream_t st);
+
 // ---- block reductions and the distance mask (vb_block.cu) --------------------------------------
 // reduction codes of vb200_block_aggregate (mirrored in include/verde_b200.h)
 #define VB_REDUCE_MEAN 0
