@@ -231,9 +231,15 @@ def column_scale(jac):
     return scale
 
 
+# scipy.linalg.lstsq's cond in the damping=None branch = LinearRegression.tol's default in scikit-learn 1.9.0,
+# the version the goldens were made with (tests/golden/damping_none.npz stores it as ``lstsq_cond``)
+LSTSQ_COND = 1e-6
+
+
 def least_squares(jac, data, weights, damping):
     """
-    Explicit-algebra restatement of ``verde.base.least_squares`` (damped branch).
+    Explicit-algebra restatement of ``verde.base.least_squares``: the damped branch below, and
+    ``damping=None`` as a truncated SVD (see the comment in the body).
 
     ``Js = jac / s``;  rows rescaled by sqrt(w);  primal
     ``(Js^T Js + damping I) c = Js^T d`` solved with
@@ -243,8 +249,6 @@ def least_squares(jac, data, weights, damping):
     """
     import scipy.linalg
 
-    if damping is None:
-        raise ValueError("the oracle restates the damped branch only (SURVEY.md fact 6)")
     jac = np.array(jac, dtype=np.float64, copy=True)
     d = np.array(np.ravel(data), dtype=np.float64, copy=True)
     n, m = jac.shape
@@ -254,6 +258,14 @@ def least_squares(jac, data, weights, damping):
         sw = np.sqrt(np.asarray(np.ravel(weights), dtype=np.float64))
         jac *= sw[:, None]
         d *= sw
+    if damping is None:
+        # verde/base/least_squares.py:65-66 -> LinearRegression(fit_intercept=False) ->
+        # scipy.linalg.lstsq(X, y, cond=LinearRegression.tol) (sklearn/linear_model/_base.py, scikit-learn 1.9):
+        # LAPACK gelsd = minimum-norm solution over the singular values sigma > cond * sigma_max
+        u, sv, vt = np.linalg.svd(jac, full_matrices=False)
+        keep = sv > LSTSQ_COND * sv[0]
+        coef = vt[keep].T @ ((u[:, keep].T @ d) / sv[keep])
+        return coef / scale
     if m > n:
         kernel = jac @ jac.T
         kernel.flat[:: n + 1] += damping
@@ -269,12 +281,12 @@ def least_squares(jac, data, weights, damping):
 
 def least_squares_sklearn(jac, data, weights, damping):
     """The literal call sequence of verde/base/least_squares.py:63-70."""
-    from sklearn.linear_model import Ridge
+    from sklearn.linear_model import LinearRegression, Ridge
     from sklearn.preprocessing import StandardScaler
 
     scaler = StandardScaler(copy=True, with_mean=False, with_std=True)
     jac = scaler.fit_transform(np.asarray(jac, dtype=np.float64))
-    regr = Ridge(alpha=damping, fit_intercept=False)
+    regr = LinearRegression(fit_intercept=False) if damping is None else Ridge(alpha=damping, fit_intercept=False)
     regr.fit(jac, np.ravel(data), sample_weight=weights)
     return regr.coef_ / scaler.scale_
 

@@ -124,10 +124,84 @@ def test_least_squares_explicit_jacobian(vb, golden_spline, oracle):
     assert np.max(np.abs(params - ref)) / np.max(np.abs(ref)) <= force_tol(cond)
 
 
-def test_damping_none_is_refused(vb, golden_spline):
+def checker_sample(size):
+    rng = np.random.RandomState(0)
+    e, n = rng.uniform(0, 5000, size), rng.uniform(-5000, 0, size)
+    return e, n, 1000.0 * np.sin((2 * np.pi / 2500.0) * e) * np.cos((2 * np.pi / 2500.0) * n)
+
+
+@pytest.mark.parametrize("tag,size", [("n240", 240), ("n1500", 1500)])
+def test_damping_none_matches_reference(vb, tag, size):
+    """
+    SURVEY 8f rank 3, the reference's default ``Spline()``: verde/base/least_squares.py:65-70 ->
+    LinearRegression -> scipy.linalg.lstsq(cond=1e-6) (scikit-learn 1.9.0, stored in the golden).  The truncation
+    is the regulariser here (rank 210 of 240, 270 of 1500) and the singular values next to the cut are ~1 % apart,
+    so the kept set must be identical; the forces then agree to ~eps * sigma_max / gap.
+    """
+    from conftest import load_golden
+
+    g = load_golden("damping_none.npz")
+    e, n, d = checker_sample(size)
+    np.testing.assert_array_equal(e[:16], g["east_head_" + tag])
+    sp = vb.Spline().fit((e, n), d)
+    info = sp.fit_info_
+    assert info["svd_rank"] == int(g["rank_" + tag]), info
+    sv = g["singular_" + tag]
+    assert abs(info["sigma_max"] / sv[0] - 1) < 1e-12 and abs(info["sigma_min_kept"] / sv[info["svd_rank"] - 1] - 1) < 1e-6
+    ref = g["force_" + tag]
+    ferr = np.max(np.abs(sp.force_ - ref)) / np.max(np.abs(ref))
+    grid = vb.grid_coordinates((0, 5000, -5000, 0), shape=(23, 29))
+    gerr = np.max(np.abs(sp.predict(grid) - g["grid_" + tag])) / np.ptp(d)
+    record_parity("damping_none_" + tag, dict(force=ferr, grid=gerr, rank=info["svd_rank"], sweeps=info["svd_sweeps"],
+                                              solve_ms=info["solve_ms"], cond_kept=info["cond_est"]))
+    assert ferr <= 1e-6 and gerr <= 1e-6, (ferr, gerr, info)
+    assert abs(sp.score((e, n), d) - float(g["score_" + tag])) <= 1e-9
+
+
+def test_damping_none_weighted_separate_forces_underdetermined_and_elastic(vb):
+    from conftest import load_golden
+
+    g = load_golden("damping_none.npz")
+    e, n, d = checker_sample(1500)
+    w = np.random.RandomState(1).uniform(0.1, 10, e.size)
+    grid = vb.grid_coordinates((0, 5000, -5000, 0), shape=(23, 29))
+    observed = {}
+    with pytest.warns(UserWarning, match="Weights might have no effect if no regularization is used"):
+        sp = vb.Spline(force_coords=(g["fc_east"], g["fc_north"])).fit((e, n), d, weights=w)
+    assert sp.fit_info_["svd_rank"] == int(g["rank_fc_w"])
+    observed["fc_w"] = (float(np.max(np.abs(sp.force_ - g["force_fc_w"])) / np.max(np.abs(g["force_fc_w"]))),
+                        float(np.max(np.abs(sp.predict(grid) - g["grid_fc_w"])) / np.ptp(d)))
+    e, n, d = checker_sample(240)
+    with pytest.warns(UserWarning, match="Under-determined problem"):
+        sp = vb.Spline(force_coords=(e, n)).fit((e[:50], n[:50]), d[:50])
+    assert sp.fit_info_["svd_rank"] <= 50
+    observed["under"] = (float(np.max(np.abs(sp.force_ - g["force_under"])) / np.max(np.abs(g["force_under"]))),
+                         float(np.max(np.abs(sp.predict(grid) - g["grid_under"])) / np.ptp(d)))
+    region = (0, 500e3, 0, 500e3)
+    se, sn = vb.scatter_points(region, 150, random_state=0)
+    ue = 10 * np.sin(2 * np.pi * se / 3e5) * np.cos(2 * np.pi * sn / 4.5e5) + 3
+    un = -7 * np.cos(2 * np.pi * se / 4.5e5) * np.sin(2 * np.pi * sn / 3e5) + 1
+    vs = vb.VectorSpline2D().fit((se, sn), (ue, un))  # the reference's default constructor
+    assert vs.fit_info_["svd_rank"] == int(g["rank_vector"]) == 300
+    ge, gn = vs.predict(vb.grid_coordinates(region, shape=(11, 13)))
+    observed["vector"] = (float(np.max(np.abs(vs.force_ - g["force_vector"])) / np.max(np.abs(g["force_vector"]))),
+                          float(max(np.max(np.abs(ge - g["grid_east_vector"])) / np.ptp(ue),
+                                    np.max(np.abs(gn - g["grid_north_vector"])) / np.ptp(un))))
+    record_parity("damping_none_variants", observed)
+    for tag, (ferr, gerr) in observed.items():
+        assert ferr <= 1e-6 and gerr <= 1e-6, observed
+
+
+def test_damping_none_explicit_jacobian_and_cv(vb, golden_spline):
+    "least_squares(jac, d, w, damping=None) == Spline().fit; SplineCV accepts None among its dampings (verde/tests/test_spline.py:33)"
     g = golden_spline
-    with pytest.raises(NotImplementedError, match="damping=None"):
-        vb.Spline().fit((g["east"], g["north"]), g["data"])
+    e, n, d = g["east"], g["north"], g["data"]
+    sp = vb.Spline().fit((e, n), d)
+    params = vb.least_squares(sp.jacobian((e, n), (e, n)), d, None, damping=None)
+    np.testing.assert_allclose(params, sp.force_, rtol=0, atol=1e-9 * np.max(np.abs(sp.force_)))
+    cv = vb.SplineCV(dampings=[None, 1e3]).fit((e, n), d)
+    assert cv.damping_ is None and cv.scores_.shape == (2,)
+    np.testing.assert_allclose(cv.force_, sp.force_, rtol=0, atol=1e-9 * np.max(np.abs(sp.force_)))
 
 
 def test_not_positive_definite_reports_pivot(vb):

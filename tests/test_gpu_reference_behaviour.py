@@ -1,8 +1,11 @@
 """
 The reference's OWN behavioural tests for this path (verde/tests/test_spline.py, test_vector.py,
-test_model_selection.py), restated against verde_b200 with the same data and the same tolerances.  Only the
-``damping=None`` variants are adapted: that branch is outside the path, so the tests that use
-the un-damped default run with a small positive damping instead and say so.
+test_model_selection.py), restated against verde_b200 with the same data and the same tolerances.  The variants
+that use the un-damped default (``damping=None``) are kept twice: with a small positive damping, where the
+reference's "exact interpolation" tolerances hold, and with ``damping=None`` itself
+(``test_default_constructors_behave_like_the_pinned_reference``) against what the unmodified reference produces in
+the pinned environment -- under scikit-learn 1.9 ``LinearRegression`` truncates at 1e-6 sigma_max, so the
+reference's own rtol=1e-5 assertions fail there too (max miss 113 on test_spline's data).
 """
 import warnings
 
@@ -204,3 +207,32 @@ def test_cross_val_score_of_a_vector_of_splines(vb):
     scores = vb.cross_val_score(vb.Spline(damping=1e-10), coords, data, cv=ShuffleSplit(n_splits=3, random_state=0))
     assert len(scores) == 3
     npt.assert_allclose(scores, 1, atol=1e-3)
+
+
+def test_default_constructors_behave_like_the_pinned_reference(vb):
+    """
+    verde/tests/test_spline.py:33-99 and test_vector.py:31-40 with the reference's own ``damping=None``.  Expected
+    values: the unmodified reference run here with scikit-learn 1.9.0 / scipy 1.18.1 (oracle/_refimport.py):
+    Spline() on test_spline's data scores 0.998547768467705 (max miss 113.1); SplineCV([None, 1e3]) picks None with
+    scores [9.96846484e-01, 7.80646073e-04]; VectorSpline2D() interpolates (full rank, max miss 6e-9).
+    """
+    region = (100, 500, -800, -700)
+    synth = vb.CheckerBoard(region=region)
+    data = synth.scatter(size=1500, random_state=1)
+    coords = (data.easting, data.northing)
+    spline = vb.Spline().fit(coords, data.scalars)
+    npt.assert_allclose(spline.score(coords, data.scalars), 0.998547768467705, atol=1e-8)
+    npt.assert_allclose(np.max(np.abs(spline.predict(coords) - data.scalars)), 113.11381572345215, rtol=1e-5)
+    assert data.scalars.size == spline.force_.size
+    data = synth.scatter(size=1500, random_state=0)
+    coords = (data.easting, data.northing)
+    cv = vb.SplineCV(dampings=[None, 1e3], cv=ShuffleSplit(n_splits=1, random_state=0)).fit(coords, data.scalars)
+    assert cv.damping_ is None
+    npt.assert_allclose(cv.scores_, [9.96846484e-01, 7.80646073e-04], rtol=1e-6)
+    synth = vb.CheckerBoard()
+    coordinates = vb.grid_coordinates(synth.region, shape=(15, 20))
+    data2 = tuple(synth.predict(coordinates).ravel() for i in range(2))
+    flat = tuple(i.ravel() for i in coordinates)
+    vector = vb.VectorSpline2D().fit(flat, data2)
+    npt.assert_allclose(vector.score(flat, data2), 1, atol=1e-5)
+    npt.assert_allclose(vector.predict(flat), data2, rtol=1e-2, atol=1)  # the reference's tolerance

@@ -59,8 +59,10 @@ def test_fit_input_validation_errors():
 def test_weights_without_damping_warns_like_reference():
     e = np.linspace(0, 1, 8)
     with pytest.warns(UserWarning, match="Weights might have no effect if no regularization is used"):
-        with pytest.raises((NotImplementedError, vb.EngineError)):
-            vb.Spline().fit((e, e), e, weights=np.ones(8))
+        try:
+            vb.Spline().fit((e, e), e, weights=np.ones(8))  # damping=None: the truncated-SVD solve (GPU only)
+        except vb.EngineError:
+            pass  # no CUDA device here: the warning must still have been issued before the engine is reached
 
 
 def test_predict_before_fit_raises_not_fitted():

@@ -158,6 +158,8 @@ def raise_status(rc, what, msg):
         raise MemoryError("{}: out of device memory: {}".format(what, msg))
     if rc == E_BADARG:
         raise ValueError("{}: {}".format(what, msg))
+    if rc == E_NOCONV:
+        raise np.linalg.LinAlgError("{}: {}".format(what, msg))
     raise EngineError("{}: {}".format(what, msg))
 
 

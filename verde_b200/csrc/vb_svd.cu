@@ -18,9 +18,11 @@
 //   * pairs are visited in round-robin (tournament) order: m - 1 rounds of m / 2 DISJOINT pairs per sweep, one
 //     CTA per pair, one launch per round; a CTA keeps its two columns in shared memory (<= 13 000 rows) between
 //     the dot-product pass and the rotation pass;
-//   * a pair is rotated when |a_p . a_q| > sqrt(rows) eps ||a_p|| ||a_q|| (LAPACK dgesvj's criterion) unless BOTH
-//     columns are below 1e-9 of the largest column: those belong to the discarded part of the spectrum (the cut
-//     is at 1e-6) and their mutual orthogonality cannot matter, while rounding noise would keep them rotating;
+//   * a pair is rotated when |a_p . a_q| > max(rows, cols) eps ||a_p|| ||a_q|| (LAPACK dgesvj's criterion, CTOL = M)
+//     unless BOTH columns are below 1e-9 of the largest column: those belong to the discarded part of the spectrum
+//     (the cut is at 1e-6) and their mutual orthogonality cannot matter;
+//   * strongly graded pairs (norm ratio < sqrt(eps)) update the small column only (dgesvj's graded branch), so
+//     numerically-zero columns -- every rank-deficient spline Jacobian has them -- cannot keep the large ones rotating;
 //   * sweeps repeat until one passes without a rotation.
 //
 // Bound: HBM/L2 streaming of the column pairs (each round reads and writes the whole stacked matrix once):
@@ -100,6 +102,28 @@ vb_jacobi_round_kernel(double *__restrict__ A, long long L, long long rows, int 
     if (al <= tiny2 && be <= tiny2) return;                  // both far below the truncation level
     if (!(fabs(ga) > tol * sqrt(al) * sqrt(be))) return;     // already orthogonal
     if (threadIdx.x == 0) atomicAdd(rotations, 1u);
+    // Strongly graded pair (norm ratio below sqrt(eps)): a rotation would change the large column only by
+    // rounding noise -- thousands of such no-op updates per sweep are what keeps numerically-zero columns from
+    // ever settling.  Like LAPACK dgesvj's graded branch, only the SMALL column is updated (a Gram-Schmidt step:
+    // the rotation with its O(ratio^2) <= eps effect on the large column dropped).
+    const double eps = 2.220446049250313e-16;
+    if (be < eps * al || al < eps * be) {
+        const bool p_large = be < al;
+        const double mu = p_large ? ga / al : ga / be;
+        for (long long i = threadIdx.x; i < L; i += JAC_THREADS) {
+            double x, y;
+            if (CACHE && i < rows) {
+                x = sp[i];
+                y = sq[i];
+            } else {
+                x = ap[i];
+                y = aq[i];
+            }
+            if (p_large) aq[i] = fma(-mu, x, y);
+            else ap[i] = fma(-mu, y, x);
+        }
+        return;
+    }
     // Rutishauser's formulas: t = tan of the rotation angle, |t| <= 1
     const double zeta = (be - al) / (2.0 * ga);
     const double t = (zeta == 0.0) ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -309,7 +333,9 @@ cudaError_t vb_svd_solve(const double *jac, const double *data, const double *we
     vb_svd_identity_kernel<<<(unsigned)(((long long)mp * cols + 255) / 256), 256, 0, st>>>(rows, cols, mp, L, A);
     vb_launch_counter += 2;
     // ---- sweeps ----
-    const double tol = sqrt((double)rows) * 2.220446049250313e-16;
+    // LAPACK dgesvj's default: CTOL = number of rows, a pair counts as orthogonal below CTOL * eps (here the longer
+    // side, because the under-determined case has more columns than rows)
+    const double tol = (double)(rows > cols ? rows : cols) * 2.220446049250313e-16;
     const size_t cache_bytes = sizeof(double) * 2 * (size_t)L;
     const bool cache = cache_bytes <= 200 * 1024;
     if (cache) {

@@ -38,7 +38,8 @@ class VectorSpline2D(BaseGridder):
     mindist : float
         Added to every data-force distance (default 10e3, as the reference).
     damping : float
-        Positive damping of the column-scaled system (``None`` unsupported here).
+        Positive damping of the column-scaled system, or ``None`` (the reference default) for the
+        truncated-SVD minimum-norm solution (``kernels.LSTSQ_COND``).
     force_coords : None or tuple of arrays
     engine : str
         Deprecated, accepted for compatibility.

@@ -114,14 +114,16 @@ def predict_2d_b200(east, north, force_east, force_north, mindist, poisson, forc
     return vec_east, vec_north
 
 
+# scipy.linalg.lstsq's ``cond`` in the damping=None branch: scikit-learn >= 1.9 passes ``LinearRegression.tol``,
+# whose default is 1e-6 (sklearn/linear_model/_base.py; the goldens in tests/golden/damping_none.npz were made
+# with it).  Older scikit-learn passed None (machine precision); set this to reproduce those versions.
+LSTSQ_COND = 1e-6
+
+
 def _require_damping(damping):
+    "The Cholesky (normal-equation) entry points need a positive damping; damping=None goes through ``*_lstsq``."
     if damping is None:
-        raise NotImplementedError(
-            "damping=None (un-regularised least squares) is outside the B200 hot path: the "
-            "reference solves it with a scikit-learn-version-dependent truncated SVD "
-            "(sklearn LinearRegression -> scipy.linalg.lstsq(cond=...)); see DESIGN.md. "
-            "Pass a positive damping."
-        )
+        raise ValueError("this entry point solves the damped normal equations: damping must be a positive float")
     if not damping > 0:
         raise ValueError("damping must be positive, got {!r}".format(damping))
 
@@ -134,27 +136,33 @@ def _warn_underdetermined(ndata, nparams):
 
 def least_squares(jacobian, data, weights, damping=None, copy_jacobian=False):  # noqa: U100
     """
-    Damped weighted least squares on an explicit Jacobian, on the GPU.
+    Weighted least squares on an explicit Jacobian, on the GPU (verde/base/least_squares.py:17-71).
 
-    Same algebra as the reference (column scaling by the population standard
-    deviation, ``(Js^T W Js + damping I) c = Js^T W d``, parameters unscaled on
-    return).  The Jacobian is never modified, so *copy_jacobian* is accepted for
-    signature compatibility only.
+    Same algebra as the reference: column scaling by the population standard deviation, then
+    ``(Js^T W Js + damping I) c = Js^T W d`` by Cholesky for a positive *damping*, or -- ``damping=None`` -- the
+    minimum-norm solution of ``sqrt(W) Js c = sqrt(W) d`` with singular values below ``LSTSQ_COND * sigma_max``
+    dropped (what scikit-learn's ``LinearRegression`` computes); parameters unscaled on return.  The Jacobian
+    is never modified, so *copy_jacobian* is accepted for signature compatibility only.
     """
     lib = _cabi.require_device()
     jacobian = np.ascontiguousarray(jacobian, dtype=np.float64)
     if jacobian.ndim != 2:
         raise ValueError("jacobian must be 2-D")
     _warn_underdetermined(*jacobian.shape)
-    _require_damping(damping)
+    if damping is not None:
+        _require_damping(damping)
     d = _cabi.f64(data)
     if d.size != jacobian.shape[0]:
         raise ValueError("data size {} does not match the Jacobian rows {}".format(d.size, jacobian.shape[0]))
     w = None if weights is None else _cabi.f64(weights)
     params = np.empty(jacobian.shape[1], dtype=np.float64)
     info = _cabi.FitInfo()
-    rc = lib.vb200_least_squares(_cabi.ptr(jacobian), jacobian.shape[0], jacobian.shape[1], _cabi.ptr(d),
-                                 _cabi.ptr(w), float(damping), _cabi.ptr(params), ctypes.byref(info))
+    if damping is None:
+        rc = lib.vb200_least_squares_lstsq(_cabi.ptr(jacobian), jacobian.shape[0], jacobian.shape[1], _cabi.ptr(d),
+                                           _cabi.ptr(w), float(LSTSQ_COND), _cabi.ptr(params), ctypes.byref(info))
+    else:
+        rc = lib.vb200_least_squares(_cabi.ptr(jacobian), jacobian.shape[0], jacobian.shape[1], _cabi.ptr(d),
+                                     _cabi.ptr(w), float(damping), _cabi.ptr(params), ctypes.byref(info))
     _remember(info)
     _cabi.check(rc, "least_squares")
     return params
@@ -165,13 +173,19 @@ def fit_spline(east, north, data, weights, force_east, force_north, mindist, dam
     lib = _cabi.require_device()
     e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
     _warn_underdetermined(e.size, fe.size)
-    _require_damping(damping)
+    if damping is not None:
+        _require_damping(damping)
     w = None if weights is None else _cabi.f64(weights)
     force = np.empty(fe.size, dtype=np.float64)
     info = _cabi.FitInfo()
-    rc = lib.vb200_spline_fit(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
-                              _cabi.ptr(fn), fe.size, float(mindist), float(damping), _cabi.ptr(force),
-                              ctypes.byref(info))
+    if damping is None:
+        rc = lib.vb200_spline_fit_lstsq(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+                                        _cabi.ptr(fn), fe.size, float(mindist), float(LSTSQ_COND), _cabi.ptr(force),
+                                        ctypes.byref(info))
+    else:
+        rc = lib.vb200_spline_fit(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+                                  _cabi.ptr(fn), fe.size, float(mindist), float(damping), _cabi.ptr(force),
+                                  ctypes.byref(info))
     _remember(info)
     _cabi.check(rc, "Spline.fit")
     return force
@@ -182,13 +196,19 @@ def fit_spline_2d(east, north, data, weights, force_east, force_north, mindist, 
     lib = _cabi.require_device()
     e, n, d, fe, fn = (_cabi.f64(a) for a in (east, north, data, force_east, force_north))
     _warn_underdetermined(2 * e.size, 2 * fe.size)
-    _require_damping(damping)
+    if damping is not None:
+        _require_damping(damping)
     w = None if weights is None else _cabi.f64(weights)
     force = np.empty(2 * fe.size, dtype=np.float64)
     info = _cabi.FitInfo()
-    rc = lib.vb200_spline_fit_2d(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
-                                 _cabi.ptr(fn), fe.size, float(mindist), float(poisson), float(damping),
-                                 _cabi.ptr(force), ctypes.byref(info))
+    if damping is None:
+        rc = lib.vb200_spline_fit_2d_lstsq(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+                                           _cabi.ptr(fn), fe.size, float(mindist), float(poisson), float(LSTSQ_COND),
+                                           _cabi.ptr(force), ctypes.byref(info))
+    else:
+        rc = lib.vb200_spline_fit_2d(_cabi.ptr(e), _cabi.ptr(n), _cabi.ptr(d), _cabi.ptr(w), e.size, _cabi.ptr(fe),
+                                     _cabi.ptr(fn), fe.size, float(mindist), float(poisson), float(damping),
+                                     _cabi.ptr(force), ctypes.byref(info))
     _remember(info)
     _cabi.check(rc, "VectorSpline2D.fit")
     return force
@@ -415,6 +435,14 @@ def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindi
     """
     from . import dist
 
+    if damping is None:
+        # the truncated-SVD branch has no row-additive form: every rank solves the whole (modest) system itself,
+        # deterministically, so all ranks hold bit-identical forces without a collective
+        if kind == 1:
+            stacked_w = None if weights is None else np.concatenate([_cabi.f64(c) for c in weights])
+            return fit_spline_2d(east, north, np.concatenate([_cabi.f64(c) for c in data]), stacked_w, force_east,
+                                 force_north, mindist, poisson, None)
+        return fit_spline(east, north, data, weights, force_east, force_north, mindist, None)
     e, n, fe, fn = (_cabi.f64(a) for a in (east, north, force_east, force_north))
     a, b = dist.shard_bounds(e.size)
     if kind == 1:

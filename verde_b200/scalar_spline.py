@@ -20,9 +20,10 @@ reference; what changes is underneath ``fit`` / ``predict`` / ``jacobian``:
                scratch, verde/spline.py:243-255); jobs are dealt to the ranks of a
                ``torch.distributed`` group when one is initialised.
 
-``damping=None`` (the reference's default) selects scikit-learn's truncated-SVD
-least squares there, whose result depends on the scikit-learn version; it is
-outside this path and raises ``NotImplementedError`` at ``fit``.
+``damping=None`` (the reference's default) is scikit-learn's ``LinearRegression``
+there: the minimum-norm least-squares solution with singular values below
+``1e-6 * sigma_max`` dropped (scikit-learn >= 1.9).  Here it is a one-sided Jacobi
+SVD of the scaled Jacobian on the device (``vb_svd.cu``, ``kernels.LSTSQ_COND``).
 """
 import itertools
 import time
@@ -69,9 +70,9 @@ class Spline(BaseGridder):
     mindist : float or None
         Deprecated fudge factor added to every data-force distance (kept, and
         still applied, exactly like the reference).
-    damping : float
-        Positive Tikhonov damping of the column-scaled system.  ``None`` is not
-        supported on this path (see the module docstring).
+    damping : float or None
+        Positive Tikhonov damping of the column-scaled system (normal equations + Cholesky), or
+        ``None`` for the un-regularised truncated-SVD solution (see the module docstring).
     force_coords : None or tuple of arrays
         Easting and northing of the point forces; data locations when None.
     engine : str
@@ -285,8 +286,6 @@ class SplineCV(BaseGridder):
             raise NotImplementedError("delayed=True needs dask, which is outside the B200 path")
         parse_engine(self.engine)
         combos = list(itertools.product(self.mindists, self.dampings))
-        if any(damping is None for _, damping in combos):
-            kernels._require_damping(None)
         coords_c, data_c, weights_c = check_fit_input(coordinates, data, weights, unpack=False)
         cv = self.cv if self.cv is not None else KFold(shuffle=True, random_state=0, n_splits=5)
         feature_matrix = np.transpose(n_1d_arrays(coords_c, 2))
@@ -318,8 +317,16 @@ class SplineCV(BaseGridder):
                 system = kernels.GramSystem(force_coords[0].size)
                 system.accumulate(0, east, north, train[1][0], train_w, force_coords[0], force_coords[1],
                                   mindists[imd])
-                # all dampings of this (fold, mindist) are factored and solved side by side on the device
-                forces = system.solve_multi(east.size, dampings)
+                # all dampings of this (fold, mindist) are factored and solved side by side on the device;
+                # a None among them is the truncated-SVD solve, which shares nothing with the Gram matrix
+                damped = [k for k, damp in enumerate(dampings) if damp is not None]
+                forces = np.empty((len(dampings), force_coords[0].size))
+                if damped:
+                    forces[damped] = system.solve_multi(east.size, [dampings[k] for k in damped])
+                for k, damp in enumerate(dampings):
+                    if damp is None:
+                        forces[k] = kernels.fit_spline(east, north, train[1][0], train_w, force_coords[0],
+                                                       force_coords[1], mindists[imd], None)
             except (np.linalg.LinAlgError, MemoryError, kernels._cabi.EngineError) as exc:
                 failure = exc
                 table[imd, :, fold] = np.nan
