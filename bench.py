@@ -691,6 +691,7 @@ def main():
         "conditioning": {"cond_est": phase["info"]["cond_est"], "cond_upper": phase["info"]["cond_upper"],
                          "lambda_max": phase["info"]["lambda_max"], "lambda_min_est": phase["info"]["lambda_min_est"],
                          "backward_err": phase["info"]["backward_err"], "diag_ms_per_step": phase["info"]["diag_ms"],
+                         "power_its": phase["info"]["power_its"], "inverse_its": phase["info"]["inverse_its"],
                          "note": "A = D G D + damping I (the matrix the reference's Ridge factors); cond_est <= cond_2(A) <= "
                                  "cond_upper; backward_err = ||Js^T W (d - Js c) - damping c|| / (lambda_max ||c|| + ||Js^T W d||)"},
     }

@@ -67,6 +67,8 @@ typedef struct vb200_fit_info {
     int64_t svd_sweeps;      /* one-sided Jacobi sweeps until a sweep without rotations        */
     double sigma_max;        /* largest / smallest KEPT singular value of sqrt(W) Js           */
     double sigma_min_kept;
+    int32_t power_its;       /* iterations the condition estimate took: power (lambda_max) / inverse (lambda_min) */
+    int32_t inverse_its;
 } vb200_fit_info;
 
 /* ---- library / device -------------------------------------------------------------- */

@@ -47,6 +47,8 @@ class FitInfo(ctypes.Structure):
         ("svd_sweeps", ctypes.c_int64),
         ("sigma_max", ctypes.c_double),
         ("sigma_min_kept", ctypes.c_double),
+        ("power_its", ctypes.c_int32),
+        ("inverse_its", ctypes.c_int32),
     ]
 
     def as_dict(self):

@@ -299,7 +299,8 @@ double wall_ms()
 }
 
 // condition estimate of A = L L^T (every solve path leaves L in `L`); fills the cond fields of *info
-int diag_condition(const double *L, int T, long long cols, double damping, vb200_fit_info *info, cudaStream_t st)
+int diag_condition(const double *L, int T, long long cols, double damping, vb200_fit_info *info, cudaStream_t st,
+                   const double *solution = nullptr)
 {
     if (!info || !g_opt.fit_diagnostics) return 0;
     const double t0 = wall_ms();
@@ -309,11 +310,17 @@ int diag_condition(const double *L, int T, long long cols, double damping, vb200
     CU(ws_get("sweep_flags", sizeof(int) * 2 * T, (void **)&d_flags));
     VbCondEstimate ce;
     const long long launches0 = vb_launch_counter;
-    CU(vb_cond_estimate(L, T, cols, scratch, d_flags, st, 30, 8, &ce));
+    CU(vb_cond_estimate(L, T, cols, scratch, d_flags, st, 30, 8, solution, &ce));
+    info->power_its = ce.power_its;
+    info->inverse_its = ce.inverse_its;
     info->lambda_max = ce.lambda_max;
     info->lambda_min_est = ce.lambda_min;
-    info->cond_est = ce.lambda_min > 0.0 ? ce.lambda_max / ce.lambda_min : 0.0;
     info->cond_upper = damping > 0.0 ? ce.lambda_max / damping : 0.0;
+    info->cond_est = ce.lambda_min > 0.0 ? ce.lambda_max / ce.lambda_min : 0.0;
+    // When damping < eps * lambda_max the factor's own rounding (||A - L L^T|| ~ eps lambda_max) can push the smallest
+    // eigenvalue of L L^T below the damping; cond_2(A) itself is bounded by lambda_max / damping, so the estimate is
+    // clamped there (lambda_min_est keeps the raw Rayleigh quotient).
+    if (info->cond_upper > 0.0 && (info->cond_est > info->cond_upper || info->cond_est == 0.0)) info->cond_est = info->cond_upper;
     info->kernel_launches += vb_launch_counter - launches0;
     info->diag_ms += wall_ms() - t0;
     return 0;
@@ -824,7 +831,7 @@ int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, in
         return h_info;
     }
     if (info) info->backward_err = -1.0;
-    return diag_condition(L, T, cols, damping, info, st);
+    return diag_condition(L, T, cols, damping, info, st, rhs);  // rhs now holds the scaled solution
 }
 
 int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int64_t cols, int64_t total_rows,
@@ -1049,7 +1056,7 @@ int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, 
         return h_info;
     }
     if (info) info->backward_err = -1.0;
-    return diag_condition(chol_dev, T, cols, g_step.damping, info, st);
+    return diag_condition(chol_dev, T, cols, g_step.damping, info, st, rhs);
 }
 
 // ---- block reductions and the distance mask (kernels in vb_block.cu) -------

@@ -236,8 +236,11 @@ long long vb_diag_scratch_doubles(int T)
     return vb_num_tiles(T) * VB_TILE + 3LL * T * VB_TILE + 8;
 }
 
+// x0 (optional, T*128 doubles, padding zero): start vector of the inverse iteration.  The solve paths pass the
+// scaled solution c = A^-1 rhs they just computed -- already one inverse-iteration step away from rhs, and on
+// the ill-conditioned spline systems dominated by the smallest eigenvectors -- which saves sweeps over L.
 cudaError_t vb_cond_estimate(const double *L, int T, long long cols, double *scratch, int *flags, cudaStream_t st,
-                             int max_power, int max_inverse, VbCondEstimate *out)
+                             int max_power, int max_inverse, const double *x0, VbCondEstimate *out)
 {
     const long long Mpad = (long long)T * VB_TILE;
     double *partial = scratch;
@@ -272,7 +275,11 @@ cudaError_t vb_cond_estimate(const double *L, int T, long long cols, double *scr
     out->lambda_max = lam;
 
     // ---- lambda_min: inverse iteration, (L L^T) z = x by the two triangular sweeps ----
-    vb_diag_start_kernel<<<gv, 256, 0, st>>>(x, cols, Mpad, 1);
+    if (x0) {
+        if ((e = cudaMemcpyAsync(x, x0, sizeof(double) * Mpad, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+    } else {
+        vb_diag_start_kernel<<<gv, 256, 0, st>>>(x, cols, Mpad, 1);
+    }
     vb_dot2_kernel<<<1, 1024, 0, st>>>(x, x, Mpad, sc);
     vb_normalise_kernel<<<gv, 256, 0, st>>>(x, sc, Mpad, x);
     vb_launch_counter += 3;

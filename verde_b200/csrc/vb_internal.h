@@ -141,7 +141,7 @@ struct VbCondEstimate {
 long long vb_diag_scratch_doubles(int T);
 // flags: 2*T ints (the sweeps' scratch); synchronises the stream (early stopping is decided on the host)
 cudaError_t vb_cond_estimate(const double *L, int T, long long cols, double *scratch, int *flags, cudaStream_t st,
-                             int max_power, int max_inverse, VbCondEstimate *out);
+                             int max_power, int max_inverse, const double *x0, VbCondEstimate *out);
 cudaError_t vb_launch_weighted_residual(const double *d, const double *pred, const double *w, long long n, double *r,
                                         cudaStream_t st);
 // out3 = {||D grad - damping c||^2, ||c||^2, ||D J^T W d||^2} with c = force / inv_scale

@@ -47,6 +47,17 @@ def world():
     return 0, 1
 
 
+def backend():
+    "Backend name of the default process group ('nccl' / 'gloo'), or None without one."
+    try:
+        import torch.distributed as td
+    except ImportError:  # pragma: no cover
+        return None
+    if td.is_available() and td.is_initialized():
+        return td.get_backend()
+    return None
+
+
 def sharding_active():
     if _SHARDING is False:
         return False
@@ -211,3 +222,34 @@ def allgather_concat(local, total):
         a, b = shard_bounds(total, r, size)
         out[a:b] = part[: b - a].cpu().numpy()
     return out
+
+
+def gather_device_shards(compute_local, total, components=1):
+    """
+    Point-sharded compute + gather WITHOUT host round trips (NCCL backend): allocates one CUDA tensor of shape
+    ``(components, world, longest_shard)``, lets ``compute_local(views, start, stop)`` write this rank's results
+    into its own slices (``views[c]`` is the contiguous device slice of component c), all-gathers IN PLACE over
+    NVLink (``all_gather_into_tensor`` with the input aliasing the rank's slot) and copies every component to the
+    host once.  Returns a list of *components* full-length float64 numpy arrays, identical on every rank.
+    """
+    import torch
+    import torch.distributed as td
+
+    rank, size = world()
+    bounds = [shard_bounds(total, r, size) for r in range(size)]
+    longest = max(b - a for a, b in bounds)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    buf = torch.empty((components, size, longest), dtype=torch.float64, device=dev)
+    a, b = bounds[rank]
+    compute_local([buf[c, rank, : b - a] for c in range(components)], a, b)
+    outs = []
+    for c in range(components):
+        td.all_gather_into_tensor(buf[c].view(-1), buf[c, rank])
+        out = np.empty(int(total), dtype=np.float64)
+        host = torch.from_numpy(out)
+        if all(bb - aa == longest for aa, bb in bounds):
+            host.copy_(buf[c].view(-1))
+        else:
+            host.copy_(torch.cat([buf[c, r, : bb - aa] for r, (aa, bb) in enumerate(bounds)]))
+        outs.append(out)
+    return outs

@@ -482,6 +482,26 @@ def predict_sharded(east, north, force_east, force_north, mindist, forces, poiss
     from . import dist
 
     e, n = _cabi.f64(east), _cabi.f64(north)
+    if dist.backend() == "nccl":
+        # results stay on the device until the gather is done: predict writes into this rank's slot of the
+        # gathered tensor, one in-place all-gather over NVLink, one device-to-host copy per component
+        lib = _cabi.require_device()
+        fe, fn, f = (_cabi.f64(x) for x in (force_east, force_north, forces))
+
+        def compute(views, a, b):
+            if b <= a:
+                return
+            if poisson is None:
+                rc = lib.vb200_predict(_cabi.ptr(e[a:b]), _cabi.ptr(n[a:b]), b - a, _cabi.ptr(fe), _cabi.ptr(fn),
+                                       _cabi.ptr(f), f.size, float(mindist), _cabi.ptr(views[0]))
+            else:
+                rc = lib.vb200_predict_2d(_cabi.ptr(e[a:b]), _cabi.ptr(n[a:b]), b - a, _cabi.ptr(fe), _cabi.ptr(fn),
+                                          _cabi.ptr(f), fe.size, float(mindist), float(poisson),
+                                          _cabi.ptr(views[0]), _cabi.ptr(views[1]))
+            _cabi.check(rc, "sharded predict")
+
+        outs = dist.gather_device_shards(compute, e.size, components=1 if poisson is None else 2)
+        return outs[0] if poisson is None else (outs[0], outs[1])
     a, b = dist.shard_bounds(e.size)
     if poisson is None:
         local = np.empty(b - a, dtype=np.float64)
