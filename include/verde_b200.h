@@ -78,10 +78,12 @@ int vb200_device_count(void);
 int vb200_set_device(int device);
 /* tunables: "predict_exact" (0/1), "chol_panel_tiles" (1..16), "gram_slab_chunks" (1..16),
  * "gram_fused" (0/1: generate Jacobian rows in shared memory inside the Gram kernel instead of staging
- * a panel), "gemm_variant" (0/1/2/3), "gemm_strip", "predict_pts", "predict_minb", "predict_wide" (0/1),
+ * a panel), "gemm_variant" (0/1/2/3/4; 4 = persistent kernel with a dynamic tile queue), "gemm_grid_limit", "gemm_strip", "predict_pts", "predict_minb", "predict_wide" (0/1),
  * "sweep_group" (systems per batch of vb200_gram_solve_multi, 0 = as many as fit), "solve_variant",
  * "fit_diagnostics" (0/1, default 1: condition estimate + backward error after every fit) */
 int vb200_set_option(const char *key, double value);
+/* current value of a tunable (so that callers can restore it) */
+int vb200_get_option(const char *key, double *value);
 /* frees the cached device workspace (Gram matrix, panels) */
 int vb200_release_workspace(void);
 /* kernels launched by this library since it was loaded (bench.py's gpu_launches) */
@@ -186,6 +188,22 @@ int vb200_chol_panel_range(int64_t cols, int32_t k0, int32_t pw, int64_t *offset
 int vb200_chol_panel(double *chol_dev, int64_t cols, int32_t k0, int32_t pw);
 int vb200_chol_update(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, int32_t j_lo,
                       int32_t j_hi);
+/* Device buffers that the other processes of the node can map (CUDA IPC), for the peer-memory panel exchange:
+ * shared_alloc = cudaMalloc + cudaIpcGetMemHandle (handle: 64 bytes, sent to the peers by the host layer);
+ * shared_open  = cudaIpcOpenMemHandle in the CALLER's device context (the peer's buffer becomes addressable from
+ *                this GPU over NVLink); shared_close / shared_free undo them (close every mapping before freeing). */
+int vb200_shared_alloc(int64_t bytes, void **ptr, void *handle);
+int vb200_shared_free(void *ptr);
+int vb200_shared_open(const void *handle, void **ptr);
+int vb200_shared_close(void *ptr);
+/* Peer-memory panel exchange (one process per GPU on one node, buffers shared over CUDA IPC by the host layer): parks
+ * the library stream until the 64-bit word *flag_dev, which the panel's owner writes AFTER pushing the panel into this
+ * rank's matrix with a copy engine, is >= epoch.  Asynchronous; a panel that does not arrive within ~10 s makes
+ * vb200_chol_finish return VB200_E_CUDA instead of hanging. */
+int vb200_chol_wait_panel(const int64_t *flag_dev, int64_t epoch);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) for the pushes above: dst is a peer GPU's memory mapped
+ * into this process (CUDA IPC), stream a cudaStream_t of the caller (NULL = the library stream).  Asynchronous. */
+int vb200_peer_copy_async(void *dst, const void *src, int64_t bytes, void *stream);
 int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params,
                       vb200_fit_info *info);
 

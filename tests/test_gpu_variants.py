@@ -29,19 +29,28 @@ def test_gemm_generations_agree(env):
     e, nn, d = sample(1100)
     w = np.random.RandomState(1).uniform(0.5, 2, e.size)
     results = {}
+    default = vb._cabi.get_option("gemm_variant")
     try:
-        for variant in (3, 0, 1, 2):
+        for variant in (3, 0, 1, 2, 4):
             assert lib.vb200_set_option(b"gemm_variant", float(variant)) == 0
             system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, w, e, nn, 1e-5)
             gram = system.gram.cpu().numpy()
             results[variant] = (gram, system.solve(e.size, 1e-3))
+        # the dynamic tile queue with a capped grid (SMs left to a concurrent stream): same tiles, same bits
+        assert lib.vb200_set_option(b"gemm_grid_limit", 37.0) == 0
+        system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, w, e, nn, 1e-5)
+        results["4 capped"] = (system.gram.cpu().numpy(), system.solve(e.size, 1e-3))
     finally:
-        lib.vb200_set_option(b"gemm_variant", 3.0)
+        lib.vb200_set_option(b"gemm_variant", default)
+        lib.vb200_set_option(b"gemm_grid_limit", 0.0)
     g_ref, f_ref = results[3]
     for variant in (0, 1, 2):
         gram, force = results[variant]
         np.testing.assert_allclose(gram, g_ref, rtol=1e-13, atol=1e-13 * np.abs(g_ref).max())
         assert np.max(np.abs(force - f_ref)) <= 1e-9 * np.max(np.abs(f_ref)), variant
+    for variant in (4, "4 capped"):  # one add per element per launch, whichever CTA draws the tile: bit-identical
+        np.testing.assert_array_equal(results[variant][0], g_ref)
+        np.testing.assert_array_equal(results[variant][1], f_ref)
 
 
 @pytest.mark.parametrize("mindist,weighted", [(0.0, False), (1e-5, True)])
@@ -109,11 +118,15 @@ def test_batched_damping_sweep_equals_one_solve_per_damping(env, n):
         single = system.solve(e.size, damping, keep=True)
         np.testing.assert_array_equal(batched[k], single)
     # the older tile kernels walk the batch matrix by matrix: same answer
+    default = vb._cabi.get_option("gemm_variant")
     try:
         assert lib.vb200_set_option(b"gemm_variant", 1.0) == 0
         v2 = system.solve_multi(e.size, dampings[:3])
+        assert lib.vb200_set_option(b"gemm_variant", 4.0) == 0
+        v4 = system.solve_multi(e.size, dampings)
     finally:
-        lib.vb200_set_option(b"gemm_variant", 3.0)
+        lib.vb200_set_option(b"gemm_variant", default)
+    np.testing.assert_array_equal(v4, batched)  # dynamic tile queue over the batch: bit-identical
     assert np.max(np.abs(v2 - batched[:3])) <= 1e-9 * np.max(np.abs(batched[:3]))
 
 
@@ -190,3 +203,46 @@ def test_stepwise_cholesky_equals_the_fused_solve(env, n, panel_tiles):
     # misuse is refused: no begin -> no panel / finish
     assert lib.vb200_chol_panel(system.gram.data_ptr(), n, 0, 1) != 0
     assert lib.vb200_chol_panel_range(n, T, 1, ctypes.byref(off), ctypes.byref(cnt)) != 0
+
+
+@pytest.mark.parametrize("m,panel,min_rows", [(2500, 2, 4), (14_000, 8, 96)])
+def test_lookahead_cholesky_is_bit_identical(env, m, panel, min_rows):
+    """Single-GPU look-ahead: panel p+1 is factored on a few SMs beside the trailing update of panel p (two grids
+    draining one dynamic tile queue).  Every tile sees the same operands in the same order -> the same bits."""
+    vb, kernels, lib = env
+    e, nn, d = sample(m, seed=31)
+    saved = {k: vb._cabi.get_option(k) for k in ("gemm_variant", "chol_lookahead", "chol_panel_tiles", "chol_lookahead_min_rows")}
+    forces = {}
+    try:
+        lib.vb200_set_option(b"chol_panel_tiles", float(panel))
+        lib.vb200_set_option(b"chol_lookahead_min_rows", float(min_rows))
+        for tag, variant, ahead in (("static", 3, 0), ("dynamic", 4, 0), ("ahead16", 4, 16), ("ahead40", 4, 40)):
+            lib.vb200_set_option(b"gemm_variant", float(variant))
+            lib.vb200_set_option(b"chol_lookahead", float(ahead))
+            forces[tag] = kernels.fit_spline(e, nn, d, None, e, nn, 1e-5, 1e-4)
+    finally:
+        for k, v in saved.items():
+            lib.vb200_set_option(k.encode(), v)
+    for tag in ("dynamic", "ahead16", "ahead40"):
+        np.testing.assert_array_equal(forces[tag], forces["static"], err_msg=tag)
+
+
+def test_lookahead_batched_sweep_is_bit_identical(env):
+    vb, kernels, lib = env
+    e, nn, d = sample(1800, seed=33)
+    dampings = [1e-6, 1e-4, 1e-2]
+    system = kernels.GramSystem(e.size).accumulate(0, e, nn, d, None, e, nn, 0.0)
+    plain = system.solve_multi(e.size, dampings)
+    saved = {k: vb._cabi.get_option(k) for k in ("gemm_variant", "chol_lookahead", "chol_panel_tiles", "chol_lookahead_min_rows")}
+    try:
+        for k, v in (("gemm_variant", 4), ("chol_lookahead", 16), ("chol_panel_tiles", 2), ("chol_lookahead_min_rows", 4)):
+            lib.vb200_set_option(k.encode(), float(v))
+        ahead = system.solve_multi(e.size, dampings)
+        lib.vb200_set_option(b"chol_lookahead", 0.0)
+        same_panels = system.solve_multi(e.size, dampings)
+    finally:
+        for k, v in saved.items():
+            lib.vb200_set_option(k.encode(), v)
+    np.testing.assert_array_equal(ahead, same_panels)
+    # panel width 2 vs 8 only re-associates the trailing sums: the well-conditioned member (damping 1e-2) agrees closely
+    assert np.max(np.abs(ahead[2] - plain[2])) <= 1e-7 * np.max(np.abs(plain[2]))

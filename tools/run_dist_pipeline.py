@@ -1,0 +1,81 @@
+"""
+Panel-cyclic multi-GPU Cholesky: serial schedule vs look-ahead (broadcasts on a side stream beside the updates),
+under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_dist_pipeline.py [n ...]
+For each size n the all-reduced Gram matrix of a CheckerBoard sample is solved replicated, serial and look-ahead from
+the same matrix; rank 0 prints one JSON object per size (device times, max over ranks; forces compared bit for bit).
+NCCL tuning variables (NCCL_MIN_NCHANNELS, ...) are taken from the environment and echoed.
+"""
+import json, os, sys, time, warnings
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+import torch
+import torch.distributed as td
+import verde_b200 as vb
+from verde_b200 import kernels
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+vb._cabi.require_device().vb200_set_device(local)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+td.init_process_group("nccl", device_id=torch.device("cuda", local))
+sizes = [int(a) for a in sys.argv[1:]] or [3000, 20000]
+damping, mindist = 1e-6, 1e-5
+ok = True
+
+
+def timed(fn):
+    torch.cuda.synchronize(); td.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    td.all_reduce(dt, op=td.ReduceOp.MAX)
+    return float(dt.item()), out
+
+
+for n in sizes:
+    tab = vb.CheckerBoard().scatter(size=n, random_state=0)
+    e, nn, d = tab.easting.values, tab.northing.values, tab.scalars.values
+    a, b = vb.dist.shard_bounds(n)
+    system = kernels.GramSystem(n)
+    system.accumulate(0, e[a:b], nn[a:b], d[a:b], None, e, nn, mindist)
+    t_allreduce, _ = timed(system.allreduce)
+    keep = system.gram.clone()
+    res = {"n": n, "world": world, "allreduce_s": t_allreduce,
+           "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_") and k != "NCCL_DEBUG"}}
+    forces = {}
+    for rep in range(2):  # the second repetition is the warm one
+        system.gram.copy_(keep)
+        res["replicated_s"], forces["replicated"] = timed(lambda: system.solve(n, damping))
+        res["replicated_factor_ms"] = system.info.factor_ms
+        for mode in ("serial", "lookahead", "peer"):
+            vb.dist.set_panel_pipeline(mode)
+            system.info = vb._cabi.FitInfo()
+            system.gram.copy_(keep)
+            phases = {}
+            res[mode + "_s"], forces[mode] = timed(lambda: system.solve_distributed(n, damping, phase_times=phases))
+            res[mode + "_rank0_phase_ms"] = {k: round(v, 2) for k, v in phases.items()}
+            res[mode + "_factor_ms"] = system.info.factor_ms
+            # the same without per-phase events (they add host work between launches)
+            system.info = vb._cabi.FitInfo()
+            system.gram.copy_(keep)
+            res[mode + "_nomarks_s"], _ = timed(lambda: system.solve_distributed(n, damping))
+            res[mode + "_nomarks_factor_ms"] = system.info.factor_ms
+    mine = torch.from_numpy(forces["peer"]).cuda()
+    lo, hi = mine.clone(), mine.clone()
+    td.all_reduce(lo, op=td.ReduceOp.MIN); td.all_reduce(hi, op=td.ReduceOp.MAX)
+    res["ranks_agree"] = bool((lo == hi).all().item())
+    res["lookahead_vs_serial_bit_identical"] = bool(np.array_equal(forces["lookahead"], forces["serial"]))
+    res["peer_vs_serial_bit_identical"] = bool(np.array_equal(forces["peer"], forces["serial"]))
+    res["distributed_vs_replicated_bit_identical"] = bool(np.array_equal(forces["serial"], forces["replicated"]))
+    res["cond_est"], res["backward_err"] = system.info.cond_est, system.info.backward_err
+    ok = ok and res["ranks_agree"] and res["lookahead_vs_serial_bit_identical"] and res["peer_vs_serial_bit_identical"]
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    del system, keep
+td.destroy_process_group()
+sys.exit(0 if ok else 1)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "vb200_device_count": (ctypes.c_int, []),
     "vb200_set_device": (ctypes.c_int, [ctypes.c_int]),
     "vb200_set_option": (ctypes.c_int, [ctypes.c_char_p, dbl]),
+    "vb200_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(dbl)]),
     "vb200_release_workspace": (ctypes.c_int, []),
     "vb200_launch_count": (i64, []),
     "vb200_measure_fp64_peak_tflops": (dbl, [ctypes.c_int]),
@@ -82,6 +83,12 @@ SIGNATURES = {
     "vb200_chol_panel_range": (ctypes.c_int, [i64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
     "vb200_chol_panel": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_int32, ctypes.c_int32]),
     "vb200_chol_update": (ctypes.c_int, [ctypes.c_void_p, i64] + [ctypes.c_int32] * 4),
+    "vb200_shared_alloc": (ctypes.c_int, [i64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "vb200_shared_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "vb200_shared_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "vb200_shared_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "vb200_chol_wait_panel": (ctypes.c_int, [ctypes.c_void_p, i64]),
+    "vb200_peer_copy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, i64, ctypes.c_void_p]),
     "vb200_chol_finish": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_block_split": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(i64)]),
     "vb200_block_ids": (ctypes.c_int, [ctypes.c_void_p]),
@@ -130,6 +137,13 @@ def require_device():
     if lib.vb200_device_count() < 1:
         raise EngineError("verde_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback")
     return lib
+
+
+def get_option(key):
+    "Current value of a library tunable (``vb200_get_option``)."
+    value = dbl(0.0)
+    check(load().vb200_get_option(key.encode() if isinstance(key, str) else key, ctypes.byref(value)), "get_option")
+    return value.value
 
 
 def ptr(a):

@@ -51,6 +51,7 @@ struct Options {
     int sweep_group = 0;  // damped systems factored side by side in vb200_gram_solve_multi (0 = as many as fit)
     int fit_diagnostics = 1;  // condition estimate + backward error after every fit (vb_diag.cu)
     int svd_max_sweeps = 80;  // sweep limit of the damping=None Jacobi SVD (vb_svd.cu)
+    int chol_lookahead = 24;  // SMs on which panel p+1 is factored beside the trailing update of panel p (0 = off)
 } g_opt;
 
 // ---- cached workspace (grow-only, per process; one process per GPU) --------------------
@@ -171,6 +172,7 @@ double span_ms(Span &s)
 
 cudaError_t timed_gemm(const VbGemmParams &p, cudaStream_t st)
 {
+    if (p.untimed) return vb_launch_gemm(p, st);
     Span s;
     cudaError_t e = span_begin(&s, st);
     if (e != cudaSuccess) return e;
@@ -450,11 +452,39 @@ int vb200_set_option(const char *key, double value)
     else if (k == "sweep_group") g_opt.sweep_group = value < 0 ? 0 : (int)value;
     else if (k == "fit_diagnostics") g_opt.fit_diagnostics = value != 0.0;
     else if (k == "svd_max_sweeps") g_opt.svd_max_sweeps = value < 1 ? 1 : (int)value;
+    else if (k == "chol_lookahead") g_opt.chol_lookahead = value < 0 ? 0 : (int)value;
+    else if (k == "chol_lookahead_min_rows") vb_chol_lookahead_min_rows = value < 1 ? 1 : (int)value;
     else if (k == "gemm_variant") vb_gemm_variant = (int)value;
     else if (k == "gemm_strip") vb_gemm_strip = (int)value;
+    else if (k == "gemm_grid_limit") vb_gemm_grid_limit = value < 0 ? 0 : (int)value;
     else if (k == "predict_minb") vb_predict_minb = (int)value;
     else if (k == "predict_pts") vb_predict_pts = (int)value;
     else if (k == "predict_wide") vb_predict_wide = value != 0.0;
+    else return fail(VB200_E_BADARG, "unknown option '%s'", key);
+    return 0;
+}
+
+int vb200_get_option(const char *key, double *value)
+{
+    if (!key || !value) return fail(VB200_E_BADARG, "null pointer");
+    const std::string k(key);
+    if (k == "predict_exact") *value = g_opt.predict_exact;
+    else if (k == "chol_panel_tiles") *value = g_opt.chol_panel_tiles;
+    else if (k == "gram_slab_chunks") *value = g_opt.gram_slab_chunks;
+    else if (k == "solve_variant") *value = vb_solve_variant;
+    else if (k == "trsm_tiles") *value = vb_trsm_tiles;
+    else if (k == "gram_fused") *value = g_opt.gram_fused;
+    else if (k == "sweep_group") *value = g_opt.sweep_group;
+    else if (k == "fit_diagnostics") *value = g_opt.fit_diagnostics;
+    else if (k == "svd_max_sweeps") *value = g_opt.svd_max_sweeps;
+    else if (k == "gemm_variant") *value = vb_gemm_variant;
+    else if (k == "gemm_strip") *value = vb_gemm_strip;
+    else if (k == "gemm_grid_limit") *value = vb_gemm_grid_limit;
+    else if (k == "predict_minb") *value = vb_predict_minb;
+    else if (k == "predict_pts") *value = vb_predict_pts;
+    else if (k == "predict_wide") *value = vb_predict_wide;
+    else if (k == "chol_lookahead") *value = g_opt.chol_lookahead;
+    else if (k == "chol_lookahead_min_rows") *value = vb_chol_lookahead_min_rows;
     else return fail(VB200_E_BADARG, "unknown option '%s'", key);
     return 0;
 }
@@ -799,7 +829,7 @@ int vb200_gram_solve(double *gram_dev, const double *stats_dev, int64_t cols, in
     CU(span_begin(&fac, st));
     CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale, rhs, st));
     CU(vb_launch_scale_system(L, T, cols, inv_scale, damping, st));
-    CU(vb_cholesky_tiled(L, T, g_opt.chol_panel_tiles, d_info, st));
+    CU(vb_cholesky_tiled(L, T, g_opt.chol_panel_tiles, d_info, st, 1, 0, g_opt.chol_lookahead));
     CU(cudaEventRecord(fac.b, st));
     CU(span_begin(&sol, st));
     int *d_flags;
@@ -894,7 +924,7 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
         CU(cudaMemcpyAsync(damp_dev, dampings + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
         CU(span_begin(&fac, st));
         CU(vb_launch_scale_system_batched(gram_dev, T, cols, inv_scale, damp_dev, nb, Lb, stride, st));
-        CU(vb_cholesky_tiled(Lb, T, g_opt.chol_panel_tiles, d_info, st, nb, stride));
+        CU(vb_cholesky_tiled(Lb, T, g_opt.chol_panel_tiles, d_info, st, nb, stride, g_opt.chol_lookahead));
         CU(cudaEventRecord(fac.b, st));
         CU(span_begin(&sol, st));
         vb_replicate_kernel<<<dim3((unsigned)((Mpad + 255) / 256), nb), 256, 0, st>>>(rhs, Mpad, xb);
@@ -1007,6 +1037,64 @@ int vb200_chol_update(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, in
     return 0;
 }
 
+// ---- device buffers shared between the processes of one node (CUDA IPC) ---------------------------------------
+int vb200_shared_alloc(int64_t bytes, void **ptr, void *handle)
+{
+    if (bytes <= 0 || !ptr || !handle) return fail(VB200_E_BADARG, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI documents a 64-byte handle");
+    void *p = nullptr;
+    CU(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(VB200_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return 0;
+}
+
+int vb200_shared_free(void *ptr)
+{
+    if (ptr) CU(cudaFree(ptr));
+    return 0;
+}
+
+int vb200_shared_open(const void *handle, void **ptr)
+{
+    if (!handle || !ptr) return fail(VB200_E_BADARG, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    // opened in THIS rank's device context: the peer's memory becomes addressable from this GPU over NVLink
+    CU(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int vb200_shared_close(void *ptr)
+{
+    if (ptr) CU(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+int vb200_peer_copy_async(void *dst, const void *src, int64_t bytes, void *stream)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(VB200_E_BADARG, "bad copy");
+    if (bytes == 0) return 0;
+    // unified addressing resolves both sides; between two GPUs this is an NVLink peer copy on a copy engine
+    CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int vb200_chol_wait_panel(const int64_t *flag_dev, int64_t epoch)
+{
+    if (!flag_dev || !is_device_ptr(flag_dev)) return fail(VB200_E_BADARG, "the flag must be device memory");
+    int *d_info;
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    CU(vb_chol_wait_flag(reinterpret_cast<const long long *>(flag_dev), (long long)epoch, d_info, 0));
+    return 0;
+}
+
 int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, vb200_fit_info *info)
 {
     if (!g_step.open || g_step.cols != cols) return fail(VB200_E_BADARG, "vb200_chol_begin was not called for this system");
@@ -1055,6 +1143,7 @@ int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, 
         fail(h_info, "normal matrix not positive definite: pivot %d <= 0", h_info);
         return h_info;
     }
+    if (h_info < 0) return fail(VB200_E_CUDA, "a panel pushed by a peer GPU did not arrive within the time limit");
     if (info) info->backward_err = -1.0;
     return diag_condition(chol_dev, T, cols, g_step.damping, info, st, rhs);
 }
@@ -1275,7 +1364,7 @@ int vb200_gram_factor(double *gram_dev, const double *stats_dev, int64_t cols, i
     CU(span_begin(&fac, st));
     CU(vb_launch_column_scale(stats_dev, T, cols, total_rows, inv_scale_dev, rhs, st));
     CU(vb_launch_scale_system(gram_dev, T, cols, inv_scale_dev, damping, st));
-    CU(vb_cholesky_tiled(gram_dev, T, g_opt.chol_panel_tiles, d_info, st));
+    CU(vb_cholesky_tiled(gram_dev, T, g_opt.chol_panel_tiles, d_info, st, 1, 0, g_opt.chol_lookahead));
     vb_diag_minmax_kernel<<<1, 256, 0, st>>>(gram_dev, T, cols, mm);
     ++vb_launch_counter;
     CU(cudaGetLastError());

@@ -399,8 +399,20 @@ static cudaError_t chol_set_attributes(int *potrf_smem, int *trsm_smem)
 
 // Factor the outer panel of block columns [k0, k0 + pw): potrf + trsm per column and the rank-128
 // updates of the panel's own remaining columns.  Everything left of k0 must already be applied.
+static cudaError_t factor_panel_ex(double *L, int T, int k0, int pw, int *d_info, cudaStream_t stream, int batch,
+                                   long long stride, int gemm_grid_limit);
+
 cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, cudaStream_t stream, int batch,
                                  long long stride)
+{
+    return factor_panel_ex(L, T, k0, pw, d_info, stream, batch, stride, 0);
+}
+
+// gemm_grid_limit > 0: the panel's own rank-128 updates may only use that many SMs (look-ahead: the rest of the
+// machine runs the previous panel's trailing update, and a persistent grid wider than the free SMs could not finish
+// before that update does)
+static cudaError_t factor_panel_ex(double *L, int T, int k0, int pw, int *d_info, cudaStream_t stream, int batch,
+                                   long long stride, int gemm_grid_limit)
 {
     cudaError_t err;
     int potrf_smem, trsm_smem;
@@ -436,6 +448,10 @@ cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, 
             p.accumulate = 1;
             p.batch = batch;
             p.batch_stride = stride;
+            p.grid_limit = gemm_grid_limit;
+            // beside a running trailing update these launches own only a few SMs and overlap the update's own
+            // CUDA-event span: they stay out of the roofline profile (time and flops) instead of skewing it
+            p.untimed = gemm_grid_limit > 0;
             if ((err = vb_gemm_dispatch(p, stream)) != cudaSuccess) return err;
         }
     }
@@ -444,8 +460,8 @@ cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, 
 
 // Trailing update C(:, [j_lo, j_hi)) -= L(:, panel) L([j_lo, j_hi), panel)^T with the factored panel
 // [k0, k0 + pw): the bulk of the m^3/3 flops, one launch of the DMMA tile kernel (K = 128 * pw).
-cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, int j_hi, cudaStream_t stream,
-                                    int batch, long long stride)
+static cudaError_t trailing_update_ex(double *L, int T, int k0, int pw, int j_lo, int j_hi, cudaStream_t stream,
+                                      int batch, long long stride, unsigned long long *queue, int grid_limit, int untimed)
 {
     if (j_lo < k0 + pw) j_lo = k0 + pw;
     if (j_hi > T) j_hi = T;
@@ -462,23 +478,111 @@ cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, 
     p.accumulate = 1;
     p.batch = batch < 1 ? 1 : batch;
     p.batch_stride = stride;
+    p.queue = queue;
+    p.grid_limit = grid_limit;
+    p.untimed = untimed;
     return vb_gemm_dispatch(p, stream);
+}
+
+cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, int j_hi, cudaStream_t stream,
+                                    int batch, long long stride)
+{
+    return trailing_update_ex(L, T, k0, pw, j_lo, j_hi, stream, batch, stride, nullptr, 0, 0);
+}
+
+// Multi-GPU panel exchange over peer memory: the owner of a panel PUSHES it into every peer's copy of the matrix
+// with copy engines (no SM, no collective) and then writes the fit's epoch into that peer's per-panel flag word.
+// The receiver's stream parks on the flag with this one-thread kernel (system-scope acquire: the writer is another
+// GPU).  Bounded: ~10 s without the flag records -1 in *status instead of hanging the box.
+__global__ void vb_wait_flag_kernel(const long long *flag, long long value, int *status)
+{
+    long long v = 0;
+    for (unsigned spins = 0; spins < 50000000u; ++spins) {
+        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= value) return;
+        __nanosleep(200);
+    }
+    atomicCAS(status, 0, -1);
+}
+
+cudaError_t vb_chol_wait_flag(const long long *flag, long long value, int *d_info, cudaStream_t stream)
+{
+    vb_wait_flag_kernel<<<1, 1, 0, stream>>>(flag, value, d_info);
+    ++vb_launch_counter;
+    return cudaGetLastError();
 }
 
 long long vb_chol_column_offset(int c, int T) { return col_base(c, T) + (long long)c * VB_TILE_ELEMS; }
 
+// Look-ahead (single GPU).  Without it every outer panel costs ~1 ms in which 147 SMs wait for one CTA's potrf chain.
+// With `lookahead_sms` = R > 0 (needs the dynamic tile queue, gemm variant 4) panel p+1 is factored BESIDE the
+// trailing update of panel p:
+//   main stream:  U1 = update of panel p+1's own block columns (all SMs, short)
+//                 factor panel p+1                                  -> runs on the R SMs the big update leaves free
+//                 U2b = R more CTAs on the big update's tile queue  -> the freed SMs join as soon as the panel is done
+//   side stream:  U2a = update of everything right of panel p+1, grid capped at SMs - R, same tile queue as U2b
+// A 128 KB panel CTA and a 203 KB GEMM CTA cannot share an SM, so the split is exact.  Every tile is still updated
+// by exactly one CTA with the same operands in the same order: the factor is bit-identical to the plain schedule.
+int vb_chol_lookahead_min_rows = 48;  // look-ahead only while at least this many block rows remain (below, the
+                                      // panel chain is longer than the update that should hide it)
+
+static cudaError_t chol_side_stream(cudaStream_t *side, cudaEvent_t *e1, cudaEvent_t *e2)
+{
+    static cudaStream_t streams[256] = {nullptr};
+    static cudaEvent_t ev1[256] = {nullptr}, ev2[256] = {nullptr};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 256) return cudaErrorInvalidDevice;
+    if (!streams[dev]) {
+        if ((e = cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev1[dev], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev2[dev], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    *side = streams[dev];
+    *e1 = ev1[dev];
+    *e2 = ev2[dev];
+    return cudaSuccess;
+}
+
 cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream, int batch,
-                              long long stride)
+                              long long stride, int lookahead_sms)
 {
     cudaError_t err;
     if (batch < 1) batch = 1;
     if (panel_tiles < 1) panel_tiles = 1;
     if (panel_tiles > VB_MAX_KCHUNKS) panel_tiles = VB_MAX_KCHUNKS;
     if ((err = cudaMemsetAsync(d_info, 0, sizeof(int) * batch, stream)) != cudaSuccess) return err;
+    int sms = 0;
+    if ((err = vb_sm_count(&sms)) != cudaSuccess) return err;
+    const bool can_look_ahead = lookahead_sms > 0 && lookahead_sms < sms && vb_gemm_variant == 4;
+    cudaStream_t side = nullptr;
+    cudaEvent_t e1 = nullptr, e2 = nullptr;
+    if (can_look_ahead && (err = chol_side_stream(&side, &e1, &e2)) != cudaSuccess) return err;
+    bool factored = false;  // is the current panel already factored (by the previous iteration's look-ahead)?
     for (int k0 = 0; k0 < T; k0 += panel_tiles) {
         const int pw = (T - k0 < panel_tiles) ? (T - k0) : panel_tiles;
-        if ((err = vb_chol_factor_panel(L, T, k0, pw, d_info, stream, batch, stride)) != cudaSuccess) return err;
-        if ((err = vb_chol_trailing_update(L, T, k0, pw, k0 + pw, T, stream, batch, stride)) != cudaSuccess) return err;
+        if (!factored && (err = vb_chol_factor_panel(L, T, k0, pw, d_info, stream, batch, stride)) != cudaSuccess) return err;
+        factored = false;
+        const int k1 = k0 + pw;
+        if (k1 >= T) break;
+        const int pw1 = (T - k1 < panel_tiles) ? (T - k1) : panel_tiles;
+        if (can_look_ahead && T - k1 >= vb_chol_lookahead_min_rows && k1 + pw1 < T) {
+            // U1: the next panel's own columns, then its factorisation beside the rest of the update
+            if ((err = trailing_update_ex(L, T, k0, pw, k1, k1 + pw1, stream, batch, stride, nullptr, 0, 0)) != cudaSuccess) return err;
+            unsigned long long *queue = nullptr;
+            if ((err = vb_gemm_new_queue(&queue, stream)) != cudaSuccess) return err;  // zeroed before e1 in stream order
+            if ((err = cudaEventRecord(e1, stream)) != cudaSuccess) return err;
+            if ((err = cudaStreamWaitEvent(side, e1, 0)) != cudaSuccess) return err;
+            if ((err = trailing_update_ex(L, T, k0, pw, k1 + pw1, T, side, batch, stride, queue, sms - lookahead_sms, 0)) != cudaSuccess) return err;
+            if ((err = cudaEventRecord(e2, side)) != cudaSuccess) return err;
+            if ((err = factor_panel_ex(L, T, k1, pw1, d_info, stream, batch, stride, lookahead_sms)) != cudaSuccess) return err;
+            if ((err = trailing_update_ex(L, T, k0, pw, k1 + pw1, T, stream, batch, stride, queue, lookahead_sms, 1)) != cudaSuccess) return err;
+            if ((err = cudaStreamWaitEvent(stream, e2, 0)) != cudaSuccess) return err;
+            factored = true;
+        } else {
+            if ((err = vb_chol_trailing_update(L, T, k0, pw, k1, T, stream, batch, stride)) != cudaSuccess) return err;
+        }
     }
     return cudaGetLastError();
 }

@@ -472,6 +472,143 @@ vb_gemm_persistent_kernel(const VbGemmParams p, long long ntiles)
 }
 
 // ===========================================================================
+// v4: v3 with a DYNAMIC tile scheduler.  Tiles are handed out by one atomic counter in the same rasterised order
+// (so the L2 behaviour of v3 is kept); the producer warp draws the next tile id and passes it to the consumer
+// warps through a small shared-memory ring published by the full-barrier of the tile's first stage.  What it buys:
+//   * a CTA that starts late -- because a panel kernel or an NCCL kernel of another stream still holds its SM --
+//     simply draws fewer tiles instead of stalling the launch on its static share (look-ahead, multi-GPU overlap);
+//   * several launches (grids) can drain ONE queue: SMs released by a concurrent panel factorisation join in.
+// Each tile is still computed by exactly one CTA with the same arithmetic: results are bit-identical to v3.
+// ===========================================================================
+constexpr int V4_RING = 4;  // tile ids in flight between producer and consumers (the producer runs <= 1 tile ahead)
+
+__global__ void __launch_bounds__(8 * 32 + 32, 1)
+vb_gemm_dynamic_kernel(const VbGemmParams p, long long ntiles, unsigned long long *__restrict__ counter)
+{
+    constexpr int NCW = 8, MI = 8;
+    extern __shared__ __align__(128) double smem[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + V2_STAGES * V2_STAGE_DOUBLES);
+    long long *tile_ring = reinterpret_cast<long long *>(bars + 2 * V2_STAGES);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int STEPS_PER_CHUNK = VB_TILE / V2_KC;
+    const int nsteps = p.nk * STEPS_PER_CHUNK;
+    const long long total = ntiles * (p.batch > 1 ? p.batch : 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < V2_STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[V2_STAGES + s]), NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    long long gstep = 0;  // ring position, continues across tiles
+    if (warp == NCW) {
+        for (long long tcount = 0;; ++tcount) {
+            long long t = 0;
+            if (lane == 0) t = (long long)atomicAdd(counter, 1ull);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const bool done = t >= total;
+            int bi = 0, bj = 0;
+            long long moff = 0;
+            bool diag = false;
+            if (!done) {
+                const long long mat = t / ntiles;
+                decode_tile(t - mat * ntiles, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+                moff = mat * p.batch_stride;
+                diag = (bi == bj) && (p.a_base == p.b_base);
+            }
+            const unsigned stage_bytes = (diag ? 1u : 2u) * V2_KC * VB_TILE * (unsigned)sizeof(double);
+            for (int step = 0; step < (done ? 1 : nsteps); ++step, ++gstep) {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[V2_STAGES + slot]), ph ^ 1u);
+                const unsigned full = smem_u32(&bars[slot]);
+                if (step == 0 && lane == 0) tile_ring[tcount % V4_RING] = done ? -1 : t;  // published by the arrive below
+                if (done) {
+                    if (lane == 0) mbar_arrive(full);  // an empty stage: only carries the end-of-queue marker
+                    break;
+                }
+                if (lane == 0) mbar_expect_tx(full, stage_bytes);
+                __syncwarp();
+                const int kk = step / STEPS_PER_CHUNK;
+                const int krow0 = (step % STEPS_PER_CHUNK) * V2_KC;
+                double *sA = smem + slot * V2_STAGE_DOUBLES;
+                double *sB = sA + V2_KC * LDS_STRIDE;
+                const double *gA = p.a_base + moff + p.a_chunk_off[kk] + (long long)bj * VB_TILE_ELEMS + krow0 * VB_TILE;
+                const double *gB = p.b_base + moff + p.b_chunk_off[kk] + (long long)bi * VB_TILE_ELEMS + krow0 * VB_TILE;
+                bulk_load(smem_u32(sA + lane * LDS_STRIDE), gA + lane * VB_TILE, VB_TILE * sizeof(double), full);
+                if (!diag)
+                    bulk_load(smem_u32(sB + lane * LDS_STRIDE), gB + lane * VB_TILE, VB_TILE * sizeof(double), full);
+            }
+            if (done) break;
+        }
+    } else {
+        const int p0 = (warp >> 2) * (MI * 8);
+        const int q0 = (warp & 3) * 32;
+        const int lk = lane & 3, lr = lane >> 2;
+        const double alpha = p.alpha;
+        for (long long tcount = 0;; ++tcount) {
+            // the first stage of a tile also publishes its id
+            {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                mbar_wait(smem_u32(&bars[slot]), ph);
+            }
+            const long long t = tile_ring[tcount % V4_RING];
+            if (t < 0) break;
+            int bi, bj;
+            const long long mat = t / ntiles;
+            decode_tile(t - mat * ntiles, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+            const bool diag = (bi == bj) && (p.a_base == p.b_base);
+            double acc[MI][4][2];
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int step = 0; step < nsteps; ++step, ++gstep) {
+                const int slot = (int)(gstep % V2_STAGES);
+                const unsigned ph = (unsigned)(gstep / V2_STAGES) & 1u;
+                if (step > 0) mbar_wait(smem_u32(&bars[slot]), ph);
+                const double *sA = smem + slot * V2_STAGE_DOUBLES;
+                const double *sB = diag ? sA : sA + V2_KC * LDS_STRIDE;
+#pragma unroll
+                for (int k4 = 0; k4 < V2_KC / 4; ++k4) {
+                    const double *ra = sA + (k4 * 4 + lk) * LDS_STRIDE + p0 + lr;
+                    const double *rb = sB + (k4 * 4 + lk) * LDS_STRIDE + q0 + lr;
+                    double fa[MI], fb[4];
+#pragma unroll
+                    for (int a = 0; a < MI; ++a) fa[a] = ra[a * 8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) fb[b] = rb[b * 8];
+#pragma unroll
+                    for (int a = 0; a < MI; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[V2_STAGES + slot]));
+            }
+            double *ctile = p.c_base + mat * p.batch_stride + vb_tile_index(bi, bj, p.T) * VB_TILE_ELEMS;
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double *dst = ctile + (p0 + 8 * a + lr) * VB_TILE + q0 + 8 * b + 2 * lk;
+                    if (p.accumulate) {
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(alpha * acc[a][b][0]) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 1), "d"(alpha * acc[a][b][1]) : "memory");
+                    } else {
+                        *reinterpret_cast<double2 *>(dst) = make_double2(alpha * acc[a][b][0], alpha * acc[a][b][1]);
+                    }
+                }
+        }
+    }
+}
+
+// ===========================================================================
 // Fused in-shared-memory Gram (the literal north_star form): no Jacobian panel
 // anywhere in HBM.  Same persistent consumer pipeline as v3, but the stages are
 // PRODUCED by four generator warps that evaluate the Green's function
@@ -615,9 +752,35 @@ cudaError_t vb_sm_count(int *sms)
     return cudaSuccess;
 }
 // 0: v1 (cp.async + __syncthreads); 1: v2 (TMA bulk + mbarrier + bulk reduce), 8 consumer warps;
-// 2: v2 with 16 consumer warps (32x32 warp tiles); 3: v3 persistent (producer run-ahead, RED epilogue)
-int vb_gemm_variant = 3;
+// 2: v2 with 16 consumer warps (32x32 warp tiles); 3: v3 persistent (producer run-ahead, RED epilogue);
+// 4: v3 with the dynamic tile queue (default: 35.72 vs 35.58 TFLOP/s over the config-2 fit, and what look-ahead needs)
+int vb_gemm_variant = 4;
 int vb_gemm_strip = 16;  // block columns per rasterisation strip (L2 reuse of the column panels)
+
+// Tile-queue counters of the dynamic kernel: a per-device ring of zero-initialised slots; every launch takes the
+// next slot and re-zeroes the one it will meet again 512 launches later (stream-ordered, so concurrent launches
+// on different streams never share a slot).
+constexpr int V4_SMEM_BYTES = V2_SMEM_BYTES + V4_RING * (int)sizeof(long long);
+constexpr int V4_COUNTERS = 1024;
+int vb_gemm_grid_limit = 0;  // > 0: cap the persistent grid (leave SMs to a concurrent stream); 0 = all SMs
+
+cudaError_t vb_gemm_new_queue(unsigned long long **out, cudaStream_t stream)
+{
+    static unsigned long long *ring[256] = {nullptr};
+    static unsigned next[256] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 256) return cudaErrorInvalidDevice;
+    if (!ring[dev]) {
+        if ((e = cudaMalloc(&ring[dev], sizeof(unsigned long long) * V4_COUNTERS)) != cudaSuccess) return e;
+        if ((e = cudaMemset(ring[dev], 0, sizeof(unsigned long long) * V4_COUNTERS)) != cudaSuccess) return e;
+    }
+    const unsigned slot = next[dev]++ % V4_COUNTERS;
+    *out = ring[dev] + slot;
+    // this launch's slot must be zero when its kernel starts: zero it in stream order right before the launch
+    return cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream);
+}
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi)
 {
@@ -635,7 +798,7 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
     const long long tiles = vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
     if (tiles <= 0) return cudaSuccess;
     cudaError_t e;
-    if (p.batch > 1 && vb_gemm_variant != 3) {
+    if (p.batch > 1 && vb_gemm_variant != 3 && vb_gemm_variant != 4) {
         // only the persistent kernel walks a batch in one launch; the older variants go matrix by matrix
         for (int b = 0; b < p.batch; ++b) {
             VbGemmParams q = p_in;
@@ -659,6 +822,18 @@ cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
         const long long all_tiles = tiles * (p.batch > 1 ? p.batch : 1);
         const unsigned grid = (unsigned)(all_tiles < sms ? all_tiles : sms);
         vb_gemm_persistent_kernel<<<grid, 8 * 32 + 32, V2_SMEM_BYTES, stream>>>(p, tiles);
+    } else if (vb_gemm_variant == 4) {
+        int sms = 0;
+        if ((e = vb_sm_count(&sms)) != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(vb_gemm_dynamic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V4_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        unsigned long long *counter = p.queue;
+        if (!counter && (e = vb_gemm_new_queue(&counter, stream)) != cudaSuccess) return e;
+        const long long all_tiles = tiles * (p.batch > 1 ? p.batch : 1);
+        const int limit = p.grid_limit > 0 ? p.grid_limit : vb_gemm_grid_limit;
+        long long want = limit > 0 && limit < sms ? limit : sms;
+        const unsigned grid = (unsigned)(all_tiles < want ? all_tiles : want);
+        vb_gemm_dynamic_kernel<<<grid, 8 * 32 + 32, V4_SMEM_BYTES, stream>>>(p, tiles, counter);
     } else if (vb_gemm_variant == 2) {
         e = cudaFuncSetAttribute(vb_gemm_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES);
         if (e != cudaSuccess) return e;

@@ -27,10 +27,18 @@ struct VbGemmParams {
     // has every base pointer advanced by b * batch_stride doubles.  0 or 1 = a single matrix.
     int batch;
     long long batch_stride;
+    // dynamic tile queue (gemm variant 4 only).  queue == nullptr: the launch gets a fresh, zeroed counter.  Several
+    // launches given the SAME counter (vb_gemm_new_queue) drain one queue -- SMs freed by a concurrent panel
+    // factorisation join an update that is already running.  grid_limit > 0 caps the persistent grid.
+    unsigned long long *queue;
+    int grid_limit;
+    int untimed;  // 1: keep this launch out of the CUDA-event profile (the second grid of a shared queue)
 };
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
 cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream);
+// a zeroed tile-queue counter (zeroed in `stream` order) for launches that share one queue
+cudaError_t vb_gemm_new_queue(unsigned long long **queue, cudaStream_t stream);
 // same, but recorded by the API layer's CUDA-event profile (vb_api.cu)
 cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t stream);
 // SM count of the CURRENT device (cached per device ordinal: a process may switch devices)
@@ -38,7 +46,7 @@ cudaError_t vb_sm_count(int *sms);
 // every kernel launch of the library bumps this (the bench's gpu_launches claim)
 extern long long vb_launch_counter;
 // DMMA tile kernel flavour (see vb_gemm.cu)
-extern int vb_gemm_variant, vb_gemm_strip;
+extern int vb_gemm_variant, vb_gemm_strip, vb_gemm_grid_limit;
 // predict kernel tuning knobs (vb_greens.cu)
 extern int vb_predict_minb, vb_predict_pts, vb_predict_wide;
 
@@ -112,14 +120,18 @@ cudaError_t vb_launch_fused_gram(const VbFusedGramParams &p, cudaStream_t stream
 
 // Cholesky and solves on tile-packed storage (vb_chol.cu)
 // batch matrices of stride `stride` doubles are factored side by side (d_info: one int per matrix)
+// lookahead_sms > 0: factor panel p+1 on that many SMs beside the trailing update of panel p (vb_chol.cu)
 cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cudaStream_t stream,
-                              int batch = 1, long long stride = 0);
+                              int batch = 1, long long stride = 0, int lookahead_sms = 0);
+extern int vb_chol_lookahead_min_rows;
 // the two halves of one outer step of vb_cholesky_tiled, exposed for the multi-GPU panel-cyclic
 // factorisation (the owner of a panel factors it, everybody updates the columns it owns)
 cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, cudaStream_t stream,
                                  int batch = 1, long long stride = 0);
 cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, int j_hi,
                                     cudaStream_t stream, int batch = 1, long long stride = 0);
+// park `stream` until *flag >= value (written by a peer GPU); a timeout stores -1 in *d_info
+cudaError_t vb_chol_wait_flag(const long long *flag, long long value, int *d_info, cudaStream_t stream);
 // offset (doubles) of the diagonal tile of block column c: columns [c0, c1) occupy the contiguous
 // range [vb_chol_column_offset(c0), vb_chol_column_offset(c1)) of the tile-packed triangle
 long long vb_chol_column_offset(int c, int T);

@@ -121,6 +121,109 @@ def use_distributed_cholesky(block_rows, panel_tiles, size=None):
 
 
 _PANEL_EXCHANGE = "broadcast"
+_PANEL_PIPELINE = "peer"
+_COMM_STREAM = {}
+_EPOCH = [0]
+
+
+def set_panel_pipeline(mode):
+    """
+    Schedule of the panel-cyclic Cholesky:
+
+    * ``"serial"``    factor, ``ncclBroadcast``, update -- one after the other on one stream (round 1);
+    * ``"lookahead"`` the owner of the next panel updates and factors it first; ``ncclBroadcast`` on a high-priority
+      side stream beside the updates (the receivers' NCCL kernels hold SMs while they wait for the sender);
+    * ``"peer"``      (default) the same look-ahead order, but the owner PUSHES each factored panel into every peer's
+      matrix with copy engines over NVLink peer memory (CUDA IPC; next owner first) and raises a per-panel flag word;
+      receivers park their stream on the flag.  No SM is spent on communication and nobody waits in a collective.
+
+    Same arithmetic per tile in all three -> bit-identical factors.
+    """
+    global _PANEL_PIPELINE
+    if mode not in ("serial", "lookahead", "peer"):
+        raise ValueError("panel pipeline must be 'serial', 'lookahead' or 'peer'")
+    _PANEL_PIPELINE = mode
+
+
+def panel_pipeline():
+    return _PANEL_PIPELINE
+
+
+def next_epoch():
+    "A number that grows with every collective call of the panel-cyclic factorisation (identical on every rank)."
+    _EPOCH[0] += 1
+    return _EPOCH[0]
+
+
+class SharedBuffer:
+    """
+    A device buffer of this rank that the other ranks of the node can map (``vb200_shared_alloc``: cudaMalloc +
+    CUDA-IPC handle), wrapped as a torch tensor without copying.  Never freed before the process ends: the peers keep
+    it mapped (``PeerWindow``), and CUDA forbids freeing exported memory that is still mapped elsewhere.
+    """
+
+    def __init__(self, count, dtype):
+        import ctypes
+
+        import torch
+
+        from . import _cabi
+
+        lib = _cabi.require_device()
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        self.nbytes = int(count) * itemsize
+        ptr = ctypes.c_void_p()
+        self.handle = ctypes.create_string_buffer(64)
+        _cabi.check(lib.vb200_shared_alloc(self.nbytes, ctypes.byref(ptr), self.handle), "shared_alloc")
+        self.ptr = int(ptr.value)
+        typestr = {torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (self.ptr, False), "version": 2}
+        self.tensor = torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
+
+
+class PeerWindow:
+    """
+    ``window.ptr(r, name)``: device address, valid on THIS rank's GPU, of rank r's ``SharedBuffer`` *name* -- the
+    peers' buffers mapped into this process in this rank's own device context (``vb200_shared_open``), so that copies
+    into them are NVLink peer writes done by this GPU's copy engines.  Construction is collective.
+    """
+
+    def __init__(self, buffers):
+        import ctypes
+
+        import torch.distributed as td
+
+        from . import _cabi
+
+        lib = _cabi.require_device()
+        rank, size = world()
+        self.local = dict(buffers)
+        mine = {name: bytes(b.handle.raw) for name, b in self.local.items()}
+        everyone = [None] * size
+        td.all_gather_object(everyone, mine)
+        self._ptr = {}
+        for r, entry in enumerate(everyone):
+            for name, handle in entry.items():
+                if r == rank:
+                    self._ptr[(r, name)] = self.local[name].ptr
+                else:
+                    ptr = ctypes.c_void_p()
+                    _cabi.check(lib.vb200_shared_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)), "shared_open")
+                    self._ptr[(r, name)] = int(ptr.value)
+        td.barrier()
+
+    def ptr(self, r, name):
+        return self._ptr[(r, name)]
+
+
+def comm_stream():
+    "The (cached, per device) high-priority CUDA stream the panel broadcasts are issued from."
+    import torch
+
+    dev = torch.cuda.current_device()
+    if dev not in _COMM_STREAM:
+        _COMM_STREAM[dev] = torch.cuda.Stream(device=dev, priority=-1)
+    return _COMM_STREAM[dev]
 
 
 def set_panel_exchange(mode):

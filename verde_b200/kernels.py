@@ -224,16 +224,32 @@ class GramSystem:
     matrix for many dampings (``keep=True``).
     """
 
-    def __init__(self, cols):
+    def __init__(self, cols, peer_exchange=None):
         import torch
 
         self._lib = _cabi.require_device()
         self.cols = int(cols)
+        from . import dist
+
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.gram = torch.empty(self._lib.vb200_gram_doubles(self.cols), dtype=torch.float64, device=dev)
+        count = self._lib.vb200_gram_doubles(self.cols)
+        self._shared = None
+        if peer_exchange is None:
+            peer_exchange = dist.world()[1] > 1 and dist.backend() == "nccl" and dist.panel_pipeline() == "peer"
+        if peer_exchange:
+            # the matrix and the per-panel flag words live in CUDA-IPC-exportable allocations: the other ranks map
+            # them (PeerWindow, at the first panel-cyclic factorisation) and push factored panels straight into them
+            self._shared = {"gram": dist.SharedBuffer(count, torch.float64), "flags": dist.SharedBuffer(4096, torch.int64)}
+            self.gram = self._shared["gram"].tensor
+            self._flags = self._shared["flags"].tensor
+            self._flags.zero_()
+            self._epoch_src = torch.zeros(1, dtype=torch.int64, device=dev)
+        else:
+            self.gram = torch.empty(count, dtype=torch.float64, device=dev)
         self.stats = torch.empty(self._lib.vb200_stats_doubles(self.cols), dtype=torch.float64, device=dev)
         self.info = _cabi.FitInfo()
         self._torch = torch
+        self._window = None  # dist.PeerWindow onto the other ranks' (gram, flags), made by the first peer-mode factorisation
 
     def accumulate(self, kind, east, north, data, weights, force_east, force_north, mindist,
                    poisson=0.0, accumulate=False):
@@ -319,17 +335,121 @@ class GramSystem:
         # broadcast: the first failing status is remembered, this rank stops issuing its own kernels but keeps
         # taking part in every collective, and all ranks raise together after ``agree_on_status``.
         status = 0
-        for p, (k0, width, owner) in enumerate(schedule):
-            if rank == owner and status == 0:
-                status = lib.vb200_chol_panel(gram_ptr, cols, k0, width)
+        torch = self._torch
+        pipeline = dist.panel_pipeline() if len(schedule) > 1 else "serial"
+        if pipeline == "peer" and self._shared is None:
+            pipeline = "lookahead"  # this matrix was not allocated for the peer exchange
+        if pipeline == "peer":
+            # Look-ahead order + peer-memory pushes: see dist.set_panel_pipeline.  flags[p] on every rank is written
+            # by the owner of panel p (the fit's epoch) after the panel itself has landed in this rank's matrix.
+            if self._window is None:
+                self._window = dist.PeerWindow(self._shared)
+            if len(schedule) > self._flags.numel():
+                raise ValueError("too many outer panels for the peer exchange ({})".format(len(schedule)))
+            epoch = dist.next_epoch()
+            main = torch.cuda.current_stream()
+            comm = dist.comm_stream()
+            self._epoch_src.fill_(epoch)
+            seeded = torch.cuda.Event()
+            seeded.record(main)
+            comm.wait_event(seeded)
+            flag_ptr = self._flags.data_ptr()
+            comm_handle = ctypes.c_void_p(comm.cuda_stream)
+            my_gram, epoch_ptr = self.gram.data_ptr(), self._epoch_src.data_ptr()
+
+            def push(p, k0, width, ready):
+                "owner: copy panel p and then its flag into every peer, the owner of panel p+1 first"
+                lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count))
+                lo, nbytes = 8 * offset.value, 8 * count.value
+                first = schedule[p + 1][2] if p + 1 < len(schedule) else (rank + 1) % size
+                comm.wait_event(ready)
+                for r in ((first + i) % size for i in range(size)):
+                    if r != rank:
+                        lib.vb200_peer_copy_async(ctypes.c_void_p(self._window.ptr(r, "gram") + lo),
+                                                  ctypes.c_void_p(my_gram + lo), nbytes, comm_handle)
+                        lib.vb200_peer_copy_async(ctypes.c_void_p(self._window.ptr(r, "flags") + 8 * p),
+                                                  ctypes.c_void_p(epoch_ptr), 8, comm_handle)
+
+            ready = torch.cuda.Event()
+            if rank == schedule[0][2]:
+                status = lib.vb200_chol_panel(gram_ptr, cols, schedule[0][0], schedule[0][1])
+            ready.record(main)
             mark("panel")
-            lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count))
-            dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
-            mark("broadcast")
-            for q0, qwidth, qowner in schedule[p + 1:]:
-                if qowner == rank and status == 0:
-                    status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
-            mark("update")
+            for p, (k0, width, owner) in enumerate(schedule):
+                if rank == owner:
+                    push(p, k0, width, ready)
+                elif status == 0:
+                    status = lib.vb200_chol_wait_panel(ctypes.c_void_p(flag_ptr + 8 * p), epoch)
+                mark("broadcast")
+                later = schedule[p + 1:]
+                if later and later[0][2] == rank:
+                    q0, qwidth, _ = later[0]
+                    if status == 0:
+                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                    if status == 0:
+                        status = lib.vb200_chol_panel(gram_ptr, cols, q0, qwidth)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    later = later[1:]
+                    mark("panel")
+                for q0, qwidth, qowner in later:
+                    if qowner == rank and status == 0:
+                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                mark("update")
+            done = torch.cuda.Event()
+            done.record(comm)
+            main.wait_event(done)  # this rank's pushes have left before anything overwrites the matrix
+        elif pipeline == "lookahead":
+            # Look-ahead: the panel broadcasts run on a high-priority side stream beside the DMMA updates of the main
+            # (library) stream, and the owner of panel p+1 updates and factors THAT panel first, as soon as panel p has
+            # arrived, so that its broadcast is on the wire while everybody is still busy with panel p's updates.
+            main = torch.cuda.current_stream()
+            comm = dist.comm_stream()
+            last = None
+            ready = torch.cuda.Event()
+            if rank == schedule[0][2]:
+                status = lib.vb200_chol_panel(gram_ptr, cols, schedule[0][0], schedule[0][1])
+            ready.record(main)
+            mark("panel")
+            for p, (k0, width, owner) in enumerate(schedule):
+                lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count))
+                if rank == owner:
+                    comm.wait_event(ready)  # the panel is factored
+                with torch.cuda.stream(comm):
+                    dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
+                    last = torch.cuda.Event()
+                    last.record(comm)
+                if rank != owner:
+                    main.wait_event(last)  # the panel has arrived
+                mark("broadcast")
+                later = schedule[p + 1:]
+                if later and later[0][2] == rank:
+                    q0, qwidth, _ = later[0]
+                    if status == 0:
+                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                    if status == 0:
+                        status = lib.vb200_chol_panel(gram_ptr, cols, q0, qwidth)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    later = later[1:]
+                    mark("panel")
+                for q0, qwidth, qowner in later:
+                    if qowner == rank and status == 0:
+                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                mark("update")
+            main.wait_event(last)
+        else:
+            for p, (k0, width, owner) in enumerate(schedule):
+                if rank == owner and status == 0:
+                    status = lib.vb200_chol_panel(gram_ptr, cols, k0, width)
+                mark("panel")
+                lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count))
+                dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
+                mark("broadcast")
+                for q0, qwidth, qowner in schedule[p + 1:]:
+                    if qowner == rank and status == 0:
+                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                mark("update")
         params = np.empty(cols, dtype=np.float64) if out is None else out  # host array or CUDA tensor
         message = _cabi.load().vb200_last_error().decode("utf-8", "replace") if status != 0 else ""
         rc = lib.vb200_chol_finish(gram_ptr, cols, _cabi.ptr(params), ctypes.byref(self.info))
@@ -427,6 +547,26 @@ def jacobian_transpose_apply(east, north, force_east, force_north, mindist, v):
     return out
 
 
+_SHARED_SYSTEM = {}
+
+
+def _shared_system(cols):
+    """
+    The GramSystem of the row-sharded fits, kept between fits of the same size (one at a time): its matrix is the
+    10 GB allocation of the fit, and in peer mode it owns the CUDA-IPC window onto the other ranks' matrices, whose
+    set-up (handle exchange + mapping) should not be paid by every fit.
+    """
+    import torch
+
+    key = (torch.cuda.current_device(), int(cols))
+    system = _SHARED_SYSTEM.get(key)
+    if system is None:
+        _SHARED_SYSTEM.clear()  # a different size: let the old matrix go first
+        system = _SHARED_SYSTEM[key] = GramSystem(cols)
+    system.info = _cabi.FitInfo()
+    return system
+
+
 def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindist, poisson, damping):
     """
     Row-sharded fit: every rank holds the full inputs, builds the normal
@@ -458,7 +598,7 @@ def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindi
     # a rank whose accumulation fails (out of memory, bad input) must not strand the others in the all-reduce
     system, failure = None, None
     try:
-        system = GramSystem(cols)
+        system = _shared_system(cols)
         system.accumulate(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson)
     except (MemoryError, ValueError, _cabi.EngineError) as exc:  # noqa: PERF203
         failure = exc
