@@ -594,15 +594,19 @@ def main():
         sampler.start()
     launches0 = lib.vb200_launch_count()
     fit_ms, pred_ms, gemm_ms, gemm_flops, gemm_launches = [], [], 0.0, 0.0, 0
+    shared_ms, shared_flops, shared_launches = 0.0, 0.0, 0
 
     def counted_step():
-        nonlocal gemm_ms, gemm_flops, gemm_launches
+        nonlocal gemm_ms, gemm_flops, gemm_launches, shared_ms, shared_flops, shared_launches
         device_step()
         fit_ms.append(phase["fit_ms"])
         pred_ms.append(phase["predict_ms"])
         gemm_ms += phase["info"]["gemm_ms"]
         gemm_flops += phase["info"]["gemm_flops"]
         gemm_launches += phase["info"]["gemm_launches"]
+        shared_ms += phase["info"]["shared_gemm_ms"]
+        shared_flops += phase["info"]["shared_gemm_flops"]
+        shared_launches += phase["info"]["shared_gemm_launches"]
 
     total_ms = timed(counted_step, args.steps)
     launches = lib.vb200_launch_count() - launches0
@@ -665,14 +669,18 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(world, n_rank, m, args.grid),  # identical to the reference arm's config
         "cholesky": ("single GPU" if world == 1 else
-                     "panel-cyclic over {} ranks, NCCL panel broadcast".format(world) if dist_chol else
+                     "panel-cyclic over {} ranks, look-ahead, panel exchange: {}".format(
+                         world, {"peer": "copy-engine pushes into peer memory (CUDA IPC over NVLink) + flag words",
+                                 "lookahead": "ncclBroadcast on a side stream", "serial": "ncclBroadcast"}[vb.dist.panel_pipeline()])
+                     if dist_chol else
                      "replicated on every rank"),
         "fit_s": fit_s, "predict_s": pred_s, "predict_gpts_per_s": (pb - pa) * world / pred_s * 1e-9,
         "predict_gpairs_per_s": n_pairs / pred_s * 1e-9,
         "fit_phases_ms": {k: phase["info"][k] for k in ("gram_ms", "factor_ms", "solve_ms", "gemm_ms")},
         "fit_fp64_frac": algorithmic_fit_flops / fit_s * 1e-12 / peak if peak > 0 else None,
         "roofline": {
-            "kernel": "vb_gemm_persistent_kernel (persistent FP64 DMMA 128x128 tile kernel, TMA-bulk/mbarrier pipeline: Gram accumulation + Cholesky updates)",
+            "kernel": "vb_gemm_dynamic_kernel (persistent FP64 DMMA 128x128 tile kernel, TMA-bulk/mbarrier pipeline, dynamic "
+                      "tile queue: Gram accumulation + Cholesky updates)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak > 0 else None,
             "traffic": NCU_GRAM_LAUNCH_TRAFFIC_BYTES if (n_rank, m) == (50_000, 50_000) else None,
@@ -683,7 +691,16 @@ def main():
                            "(vb200_measure_fp64_peak_tflops; MEASURED_PEAKS.json has no FP64 entry)",
             "launches_per_step": gemm_launches / args.steps,
             "algorithmic_flops_per_step": gemm_flops / args.steps,
-            "share_of_step": gemm_ms / total_ms,
+            "share_of_step": (gemm_ms + shared_ms) / total_ms,
+            # look-ahead Cholesky: these launches of the same kernel ran on SMs - R of the SMs BESIDE the factorisation of
+            # the next panel (a second grid joins their tile queue when the panel is done); their spans time a kernel
+            # that owns part of the machine, so achieved/frac above are over the launches that own the GPU
+            "beside_panel_factorisation": {
+                "launches_per_step": shared_launches / args.steps, "flops_per_step": shared_flops / args.steps,
+                "ms_per_step": shared_ms / args.steps,
+                "achieved": shared_flops / (shared_ms * 1e-3) * 1e-12 if shared_ms > 0 else None,
+                "achieved_all_launches": ((gemm_flops + shared_flops) / ((gemm_ms + shared_ms) * 1e-3) * 1e-12
+                                          if gemm_ms + shared_ms > 0 else None)},
         },
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "diag_min_max": [phase["info"]["diag_min"], phase["info"]["diag_max"]],

@@ -47,7 +47,7 @@ typedef struct vb200_fit_info {
     double gram_ms;          /* device time: panel generation + Gram accumulation              */
     double factor_ms;        /* device time: scaling + Cholesky                                */
     double solve_ms;         /* device time: forward/back substitution + unscaling             */
-    double gemm_ms;          /* device time inside the DMMA tile kernel (all launches)         */
+    double gemm_ms;          /* device time inside the DMMA tile kernel (launches that own the GPU; see shared_gemm_*) */
     double gemm_flops;       /* algorithmic flops those launches performed (2*128^3 per tile-chunk) */
     int64_t gemm_launches;   /* launches of the DMMA tile kernel                               */
     int64_t kernel_launches; /* all kernel launches of this fit                                */
@@ -69,6 +69,12 @@ typedef struct vb200_fit_info {
     double sigma_min_kept;
     int32_t power_its;       /* iterations the condition estimate took: power (lambda_max) / inverse (lambda_min) */
     int32_t inverse_its;
+    /* --- look-ahead Cholesky: DMMA launches that ran BESIDE the factorisation of the next panel (on SMs - R of the
+     * SMs, joined later by a second grid on the same tile queue).  Their event spans time a kernel that owns only part
+     * of the machine, so they are reported apart from gemm_ms / gemm_flops (the roofline figures). --- */
+    double shared_gemm_ms;
+    double shared_gemm_flops;
+    int64_t shared_gemm_launches;
 } vb200_fit_info;
 
 /* ---- library / device -------------------------------------------------------------- */

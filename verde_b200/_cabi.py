@@ -49,6 +49,9 @@ class FitInfo(ctypes.Structure):
         ("sigma_min_kept", ctypes.c_double),
         ("power_its", ctypes.c_int32),
         ("inverse_its", ctypes.c_int32),
+        ("shared_gemm_ms", ctypes.c_double),
+        ("shared_gemm_flops", ctypes.c_double),
+        ("shared_gemm_launches", ctypes.c_int64),
     ]
 
     def as_dict(self):

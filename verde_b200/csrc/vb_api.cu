@@ -149,6 +149,11 @@ struct Profile {
     std::vector<Span> gemm;
     double gemm_flops = 0.0;
     long long launches = 0;
+    // launches that share the GPU with a concurrently running panel factorisation (look-ahead, untimed == 2):
+    // their spans measure a kernel that owns only part of the machine, so they are kept apart from the roofline spans
+    std::vector<Span> shared;
+    double shared_flops = 0.0;
+    long long shared_launches = 0;
     bool on = false;
 } g_prof;
 
@@ -172,16 +177,23 @@ double span_ms(Span &s)
 
 cudaError_t timed_gemm(const VbGemmParams &p, cudaStream_t st)
 {
-    if (p.untimed) return vb_launch_gemm(p, st);
+    if (p.untimed == 1) return vb_launch_gemm(p, st);
     Span s;
     cudaError_t e = span_begin(&s, st);
     if (e != cudaSuccess) return e;
     e = vb_launch_gemm(p, st);
     cudaEventRecord(s.b, st);
-    g_prof.gemm.push_back(s);
-    g_prof.gemm_flops += 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi) *
+    const double flops = 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi) *
                          (double)(p.batch > 1 ? p.batch : 1);
-    g_prof.launches += 1;
+    if (p.untimed == 2) {
+        g_prof.shared.push_back(s);
+        g_prof.shared_flops += flops;
+        g_prof.shared_launches += 1;
+    } else {
+        g_prof.gemm.push_back(s);
+        g_prof.gemm_flops += flops;
+        g_prof.launches += 1;
+    }
     return e;
 }
 
@@ -190,16 +202,24 @@ void prof_reset()
     g_prof.gemm.clear();
     g_prof.gemm_flops = 0.0;
     g_prof.launches = 0;
+    g_prof.shared.clear();
+    g_prof.shared_flops = 0.0;
+    g_prof.shared_launches = 0;
 }
 
 void prof_collect(vb200_fit_info *info)
 {
     double ms = 0.0;
     for (auto &s : g_prof.gemm) ms += span_ms(s);
+    double shared_ms = 0.0;
+    for (auto &s : g_prof.shared) shared_ms += span_ms(s);
     if (info) {
         info->gemm_ms += ms;
         info->gemm_flops += g_prof.gemm_flops;
         info->gemm_launches += g_prof.launches;
+        info->shared_gemm_ms += shared_ms;
+        info->shared_gemm_flops += g_prof.shared_flops;
+        info->shared_gemm_launches += g_prof.shared_launches;
     }
     prof_reset();
 }

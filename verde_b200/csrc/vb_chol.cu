@@ -574,7 +574,7 @@ cudaError_t vb_cholesky_tiled(double *L, int T, int panel_tiles, int *d_info, cu
             if ((err = vb_gemm_new_queue(&queue, stream)) != cudaSuccess) return err;  // zeroed before e1 in stream order
             if ((err = cudaEventRecord(e1, stream)) != cudaSuccess) return err;
             if ((err = cudaStreamWaitEvent(side, e1, 0)) != cudaSuccess) return err;
-            if ((err = trailing_update_ex(L, T, k0, pw, k1 + pw1, T, side, batch, stride, queue, sms - lookahead_sms, 0)) != cudaSuccess) return err;
+            if ((err = trailing_update_ex(L, T, k0, pw, k1 + pw1, T, side, batch, stride, queue, sms - lookahead_sms, 2)) != cudaSuccess) return err;
             if ((err = cudaEventRecord(e2, side)) != cudaSuccess) return err;
             if ((err = factor_panel_ex(L, T, k1, pw1, d_info, stream, batch, stride, lookahead_sms)) != cudaSuccess) return err;
             if ((err = trailing_update_ex(L, T, k0, pw, k1 + pw1, T, stream, batch, stride, queue, lookahead_sms, 1)) != cudaSuccess) return err;

@@ -32,7 +32,8 @@ struct VbGemmParams {
     // factorisation join an update that is already running.  grid_limit > 0 caps the persistent grid.
     unsigned long long *queue;
     int grid_limit;
-    int untimed;  // 1: keep this launch out of the CUDA-event profile (the second grid of a shared queue)
+    int untimed;  // 1: keep this launch out of the CUDA-event profile (the second grid of a shared queue);
+                  // 2: time it, but as a launch that shares the GPU with a panel factorisation (shared_gemm_*)
 };
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
