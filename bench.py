@@ -71,7 +71,7 @@ sys.path.insert(0, ROOT)
 METRIC = "spline_fit_plus_grid_predict_points_per_s@50k_forces"
 UNIT = "Mpts/s"
 DAMPING, MINDIST = 1e-6, 1e-5
-NCU_GRAM_LAUNCH_TRAFFIC_BYTES = 39.23e9  # profiles/r01_ncu_full_summary.json (29.21 GB read + 10.02 GB written)
+NCU_GRAM_LAUNCH_TRAFFIC_BYTES = 36.87e9  # profiles/r02_ncu_full_summary.json gemm_dynamic_gram_launch (26.85 GB read + 10.02 GB written)
 REGION = (0, 5000, -5000, 0)
 
 
@@ -685,8 +685,8 @@ def main():
             "frac": achieved / peak if peak > 0 else None,
             "traffic": NCU_GRAM_LAUNCH_TRAFFIC_BYTES if (n_rank, m) == (50_000, 50_000) else None,
             "traffic_note": "ncu dram__bytes_read+write of ONE Gram-accumulation launch of this kernel (76 636 tiles x K=2048 = "
-                            "5.14e12 flop, 143 ms; algorithmic HBM bytes 21e9 = read+write the 10 GB triangle + the 0.8 GB "
-                            "panel once); profiles/r01_ncu_full_summary.json r01c_gemm_v3_strip16",
+                            "5.14e12 flop, 142.9 ms; algorithmic HBM bytes 21e9 = read+write the 10 GB triangle + the 0.8 GB "
+                            "panel once); profiles/r02_ncu_full_summary.json gemm_dynamic_gram_launch",
             "peak_source": "FP64 DMMA.8x8x4 issue microbenchmark run in this process "
                            "(vb200_measure_fp64_peak_tflops; MEASURED_PEAKS.json has no FP64 entry)",
             "launches_per_step": gemm_launches / args.steps,

@@ -86,7 +86,9 @@ int vb200_set_device(int device);
  * "gram_fused" (0/1: generate Jacobian rows in shared memory inside the Gram kernel instead of staging
  * a panel), "gemm_variant" (0/1/2/3/4; 4 = persistent kernel with a dynamic tile queue), "gemm_grid_limit", "gemm_strip", "predict_pts", "predict_minb", "predict_wide" (0/1),
  * "sweep_group" (systems per batch of vb200_gram_solve_multi, 0 = as many as fit), "solve_variant",
- * "fit_diagnostics" (0/1, default 1: condition estimate + backward error after every fit) */
+ * "fit_diagnostics" (0/1, default 1: condition estimate + backward error after every fit), "cond_inverse_its" (inverse
+ * iterations of the condition estimate; 0 = automatic), "chol_lookahead" (SMs that factor panel p+1 beside the trailing
+ * update of panel p; 0 = off), "chol_lookahead_min_rows" */
 int vb200_set_option(const char *key, double value);
 /* current value of a tunable (so that callers can restore it) */
 int vb200_get_option(const char *key, double *value);

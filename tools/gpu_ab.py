@@ -38,6 +38,7 @@ for combo in itertools.product(*[v for _, v in sweeps]):
     f = out.cpu().numpy()
     if ref is None: ref = f.copy()
     dt, i = best
-    print(dict(zip([k for k, _ in sweeps], combo)), "wall %.3f s gram %.1f factor %.1f solve %.1f gemm %.1f ms -> %.2f TF; max|f-f0|/max|f0| = %.2e" % (
-        dt, i["gram_ms"], i["factor_ms"], i["solve_ms"], i["gemm_ms"], i["gemm_flops"] / i["gemm_ms"] * 1e-9,
+    print(dict(zip([k for k, _ in sweeps], combo)), "wall %.3f s gram %.1f factor %.1f solve %.1f diag %.1f (inv its %d, cond_est %.3e <= %.3e, bwd %.1e) gemm %.1f ms -> %.2f TF; max|f-f0|/max|f0| = %.2e" % (
+        dt, i["gram_ms"], i["factor_ms"], i["solve_ms"], i["diag_ms"], i["inverse_its"], i["cond_est"], i["cond_upper"], i["backward_err"],
+        i["gemm_ms"], i["gemm_flops"] / i["gemm_ms"] * 1e-9,
         np.max(np.abs(f - ref)) / np.max(np.abs(ref))), flush=True)

@@ -32,12 +32,13 @@ constexpr int POTRF_BLK = 16;
 //      pivots and multipliers with shuffles -- no CTA barrier inside the 16 pivot steps;
 //   3. every row below solves its 16 entries against that block (forward substitution, independent per row).
 // Two CTA barriers per block instead of two per column (32 per block): the kernel is pure latency, and this
-// took it from 65 us to the time of the dependent chains themselves.  The operation order per element is the
-// one a column-by-column elimination performs, so the factor is bit-identical to the previous kernel's.
+// took it from 65 us to the time of the dependent chains themselves (54 us); replacing sqrt + per-row division by
+// one rsqrt per column and multiplications (round 2) removes the longest of those chains.
 __global__ void __launch_bounds__(POTRF_THREADS)
 vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info, long long stride)
 {
     extern __shared__ __align__(16) double s[];  // s[c * 128 + r]
+    __shared__ double s_rinv[VB_TILE];           // 1 / sqrt(pivot) of every column
     const int r = threadIdx.x;
     const int lane = r & 31;
     tile += (long long)blockIdx.x * stride;  // one CTA per matrix of a batch
@@ -53,6 +54,7 @@ vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info,
 #pragma unroll
         for (int c = 0; c < POTRF_BLK; ++c) a[c] = s[(c0 + c) * VB_TILE + r];
         if (r >= c0) {  // rows above the block only hold the (ignored) upper triangle
+#pragma unroll 4
             for (int kp = 0; kp < c0; ++kp) {
                 const double lrk = s[kp * VB_TILE + r];
                 const double2 *lc = reinterpret_cast<const double2 *>(s + kp * VB_TILE + c0);
@@ -71,8 +73,15 @@ vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info,
             for (int kk = 0; kk < POTRF_BLK; ++kk) {
                 const double piv = __shfl_sync(0xffffffffu, a[kk], lo + kk);
                 if (lane == lo + kk && !(piv > 0.0)) atomicCAS(d_info, 0, k * VB_TILE + c0 + kk + 1);
-                const double l = sqrt(piv);
-                const double x = (lane == lo + kk) ? l : a[kk] / l;
+                // 1/sqrt(pivot) once per column instead of a square root followed by a division per row: the
+                // dependent sqrt + divide sequences (~350 cycles x 128 columns) were half of this kernel.  The
+                // diagonal entry gets one Newton step (l = p r, l += r/2 (p - l^2)); rows multiply by r.
+                const double rs = rsqrt(piv);
+                double x = a[kk] * rs;
+                if (lane == lo + kk) {
+                    x = fma(0.5 * rs, fma(-x, x, piv), x);
+                    s_rinv[c0 + kk] = rs;
+                }
                 a[kk] = x;
 #pragma unroll
                 for (int c = kk + 1; c < POTRF_BLK; ++c) {
@@ -92,7 +101,7 @@ vb_potrf_tile_kernel(double *__restrict__ tile, int k, int *__restrict__ d_info,
 #pragma unroll
             for (int kk = 0; kk < POTRF_BLK; ++kk) {
                 const double *lcol = s + (c0 + kk) * VB_TILE + c0;  // column c0+kk of the factored block
-                const double x = a[kk] / lcol[kk];
+                const double x = a[kk] * s_rinv[c0 + kk];
                 a[kk] = x;
 #pragma unroll
                 for (int c = kk + 1; c < POTRF_BLK; ++c) a[c] = fma(-x, lcol[c], a[c]);
@@ -279,6 +288,85 @@ __device__ __forceinline__ void flag_set(int *flag)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
 }
 
+// Diagonal-tile solves of the sweeps.  The old form (one pivot per step: divide, publish through shared memory, CTA
+// barrier -- ~300 cycles x 128 steps = 19 us) WAS the critical path of a sweep: block row i cannot finish before
+// block row i-1 has, so T x 19 us = 7.5 ms at T = 391 against 1.5 ms of HBM time for the 10 GB factor.  Now: the tile
+// is solved in four 32-row blocks; warp b solves its 32 x 32 diagonal block by substitution with the pivots exchanged
+// by shuffles (no barrier, reciprocal pivots computed once per tile: ~50 cycles per step), and one CTA barrier per
+// block lets the rows below (above, for L^T) subtract the block's 32 solved unknowns.  Still plain substitution -- no
+// explicit inverse, backward stable -- with x * (1/l) in place of x / l.
+//   forward:  st[c * 128 + r] = L(r, c);  v = right-hand side of row `tid` (threads < 128), returns y_tid
+__device__ __forceinline__ double sweep_diag_forward(const double *st, double *sv, double v, int tid)
+{
+    const int lane = tid & 31, wb = tid >> 5;
+    const double rinv = tid < VB_TILE ? 1.0 / st[tid * VB_TILE + tid] : 0.0;
+#pragma unroll 1
+    for (int b = 0; b < VB_TILE / 32; ++b) {
+        const int b0 = 32 * b;
+        if (wb == b) {
+            double lcol[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) lcol[c] = st[(b0 + c) * VB_TILE + tid];  // L(tid, b0 + c), used where lane > c
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const double yc = __shfl_sync(0xffffffffu, v * rinv, c);
+                if (lane == c) v = yc;
+                else if (lane > c) v = fma(-lcol[c], yc, v);
+            }
+            sv[tid] = v;
+        }
+        __syncthreads();
+        if (tid < VB_TILE && wb > b) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                a0 = fma(st[(b0 + c + 0) * VB_TILE + tid], sv[b0 + c + 0], a0);
+                a1 = fma(st[(b0 + c + 1) * VB_TILE + tid], sv[b0 + c + 1], a1);
+                a2 = fma(st[(b0 + c + 2) * VB_TILE + tid], sv[b0 + c + 2], a2);
+                a3 = fma(st[(b0 + c + 3) * VB_TILE + tid], sv[b0 + c + 3], a3);
+            }
+            v -= (a0 + a1) + (a2 + a3);
+        }
+    }
+    return v;
+}
+//   backward: st[r * 129 + c] = L(r, c);  solves L^T x = v, blocks and pivots in descending order
+__device__ __forceinline__ double sweep_diag_backward(const double *st, double *sv, double v, int tid)
+{
+    constexpr int LD = VB_TILE + 1;
+    const int lane = tid & 31, wb = tid >> 5;
+    const double rinv = tid < VB_TILE ? 1.0 / st[tid * LD + tid] : 0.0;
+#pragma unroll 1
+    for (int b = VB_TILE / 32 - 1; b >= 0; --b) {
+        const int b0 = 32 * b;
+        if (wb == b) {
+            double lrow[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) lrow[c] = st[(b0 + c) * LD + tid];  // L(b0 + c, tid) = L^T(tid, b0 + c), used where lane < c
+#pragma unroll
+            for (int c = 31; c >= 0; --c) {
+                const double xc = __shfl_sync(0xffffffffu, v * rinv, c);
+                if (lane == c) v = xc;
+                else if (lane < c) v = fma(-lrow[c], xc, v);
+            }
+            sv[tid] = v;
+        }
+        __syncthreads();
+        if (wb < b) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                a0 = fma(st[(b0 + c + 0) * LD + tid], sv[b0 + c + 0], a0);
+                a1 = fma(st[(b0 + c + 1) * LD + tid], sv[b0 + c + 1], a1);
+                a2 = fma(st[(b0 + c + 2) * LD + tid], sv[b0 + c + 2], a2);
+                a3 = fma(st[(b0 + c + 3) * LD + tid], sv[b0 + c + 3], a3);
+            }
+            v -= (a0 + a1) + (a2 + a3);
+        }
+    }
+    return v;
+}
+
 template <bool BACKWARD>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags, int batch, long long stride)
@@ -308,10 +396,12 @@ vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags
                 st[r * (VB_TILE + 1) + c] = dtile[idx];
             }
         }
+        // this row's right-hand side block: nobody else writes it, so it is fetched ahead of the critical path
+        const double xi = tid < VB_TILE ? x[i * VB_TILE + tid] : 0.0;
         if (!BACKWARD) {
             // y_i = L_ii^{-1} (b_i - sum_{k<i} L(i,k) y_k): thread (r, h) covers columns c = 2j + h
             const int r = tid & 127, h = tid >> 7;
-            double acc = 0.0;
+            double acc = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
             for (int k = 0; k < i; ++k) {
                 const double *tile = Lmat + vb_tile_index(i, k, T) * VB_TILE_ELEMS;
                 double l[64];
@@ -322,18 +412,19 @@ vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags
                 if (tid < VB_TILE) sv[tid] = __ldcg(x + k * VB_TILE + tid);
                 __syncthreads();
 #pragma unroll
-                for (int j = 0; j < 64; ++j) acc = fma(l[j], sv[2 * j + h], acc);
+                for (int j = 0; j < 64; j += 4) {
+                    acc = fma(l[j], sv[2 * j + h], acc);
+                    acc1 = fma(l[j + 1], sv[2 * j + 2 + h], acc1);
+                    acc2 = fma(l[j + 2], sv[2 * j + 4 + h], acc2);
+                    acc3 = fma(l[j + 3], sv[2 * j + 6 + h], acc3);
+                }
             }
-            sacc[tid] = acc;
+            sacc[tid] = (acc + acc1) + (acc2 + acc3);
             __syncthreads();
             double v = 0.0;
-            if (tid < VB_TILE) v = x[i * VB_TILE + tid] - (sacc[tid] + sacc[tid + VB_TILE]);
-            for (int c = 0; c < VB_TILE; ++c) {
-                if (tid == c) sv[c] = v / st[c * VB_TILE + c];
-                __syncthreads();
-                if (tid > c && tid < VB_TILE) v = fma(-st[c * VB_TILE + tid], sv[c], v);
-            }
-            if (tid < VB_TILE) x[i * VB_TILE + tid] = sv[tid];
+            if (tid < VB_TILE) v = xi - (sacc[tid] + sacc[tid + VB_TILE]);
+            v = sweep_diag_forward(st, sv, v, tid);
+            if (tid < VB_TILE) x[i * VB_TILE + tid] = v;
         } else {
             // x_i = L_ii^{-T} (y_i - sum_{k>i} L(k,i)^T x_k): warp w covers columns 16w..16w+15, lanes run along rows
             double acc[16];
@@ -364,13 +455,9 @@ vb_trisweep_kernel(const double *__restrict__ Lmat, int T, double *x, int *flags
             }
             __syncthreads();
             double v = 0.0;
-            if (tid < VB_TILE) v = x[i * VB_TILE + tid] - sacc[tid];
-            for (int c = VB_TILE - 1; c >= 0; --c) {
-                if (tid == c) sv[c] = v / st[c * (VB_TILE + 1) + c];
-                __syncthreads();
-                if (tid < c) v = fma(-st[c * (VB_TILE + 1) + tid], sv[c], v);
-            }
-            if (tid < VB_TILE) x[i * VB_TILE + tid] = sv[tid];
+            if (tid < VB_TILE) v = xi - sacc[tid];
+            v = sweep_diag_backward(st, sv, v, tid);
+            if (tid < VB_TILE) x[i * VB_TILE + tid] = v;
         }
         __syncthreads();
         if (tid == 0) {

@@ -299,6 +299,17 @@ cudaError_t vb_cond_estimate(const double *L, int T, long long cols, double *scr
         if (it > 0 && fabs(mu - prev) <= 1e-2 * mu) break;
     }
     out->lambda_min = mu > 0.0 ? 1.0 / mu : 0.0;
+    // The Rayleigh quotient of A itself at the last (normalised) iterate is a second upper bound on lambda_min and
+    // one half-step ahead of 1/mu: x^T A x = ||L^T x||^2 costs ONE streaming pass over the factor (a sweep pair costs
+    // ten), which is what lets the large systems stop after three inverse iterations.
+    if (out->inverse_its > 0 && mu > 0.0) {
+        if ((e = tri_matvec(true, L, T, x, partial, y, st)) != cudaSuccess) return e;
+        vb_dot2_kernel<<<1, 1024, 0, st>>>(y, y, Mpad, sc);
+        ++vb_launch_counter;
+        if ((e = cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        if (h[1] > 0.0 && h[1] < out->lambda_min) out->lambda_min = h[1];
+    }
     return cudaGetLastError();
 }
 

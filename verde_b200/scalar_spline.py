@@ -297,12 +297,13 @@ class SplineCV(BaseGridder):
         table = np.zeros((len(mindists), len(dampings), len(folds)))
         jobs = [(f, i) for f in range(len(folds)) for i in range(len(mindists))]
         sweep = {"jobs": 0, "gram_ms": 0.0, "factor_ms": 0.0, "solve_ms": 0.0, "gemm_ms": 0.0, "gemm_flops": 0.0,
-                 "score_s": 0.0}
+                 "score_s": 0.0, "split_s": 0.0, "accumulate_s": 0.0, "solve_s": 0.0}
         # A failure on one rank (a non-positive-definite system, out of memory) must not strand the others in the
         # all-reduce of the score table: the rank stops working, still joins the collective, and every rank raises.
         failure = None
         for job in dist.round_robin(len(jobs)):
             fold, imd = jobs[job]
+            t_job = time.perf_counter()
             train_index, test_index = folds[fold]
             train = tuple(select(a, train_index) for a in fit_args)
             test = tuple(select(a, test_index) for a in fit_args)
@@ -313,10 +314,14 @@ class SplineCV(BaseGridder):
                 force_coords = n_1d_arrays(self.force_coords, n=2)
             train_w = None if train[2][0] is None else train[2][0]
             kernels._warn_underdetermined(east.size, force_coords[0].size)
+            sweep["split_s"] += time.perf_counter() - t_job
             try:
+                t0 = time.perf_counter()
                 system = kernels.GramSystem(force_coords[0].size)
                 system.accumulate(0, east, north, train[1][0], train_w, force_coords[0], force_coords[1],
                                   mindists[imd])
+                sweep["accumulate_s"] += time.perf_counter() - t0
+                t0 = time.perf_counter()
                 # all dampings of this (fold, mindist) are factored and solved side by side on the device;
                 # a None among them is the truncated-SVD solve, which shares nothing with the Gram matrix
                 damped = [k for k, damp in enumerate(dampings) if damp is not None]
@@ -327,6 +332,7 @@ class SplineCV(BaseGridder):
                     if damp is None:
                         forces[k] = kernels.fit_spline(east, north, train[1][0], train_w, force_coords[0],
                                                        force_coords[1], mindists[imd], None)
+                sweep["solve_s"] += time.perf_counter() - t0
             except (np.linalg.LinAlgError, MemoryError, kernels._cabi.EngineError) as exc:
                 failure = exc
                 table[imd, :, fold] = np.nan
