@@ -196,6 +196,11 @@ int vb200_chol_panel_range(int64_t cols, int32_t k0, int32_t pw, int64_t *offset
 int vb200_chol_panel(double *chol_dev, int64_t cols, int32_t k0, int32_t pw);
 int vb200_chol_update(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, int32_t j_lo,
                       int32_t j_hi);
+/* the same update for several ascending, disjoint block-column ranges [j_lo[r], j_hi[r]) in ONE launch of the DMMA
+ * kernel (dynamic tile queue): the panels one rank owns are strided, and one launch has one tail instead of one per
+ * panel.  j_lo / j_hi are host arrays. */
+int vb200_chol_update_ranges(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, int32_t n_ranges,
+                             const int32_t *j_lo, const int32_t *j_hi);
 /* Device buffers that the other processes of the node can map (CUDA IPC), for the peer-memory panel exchange:
  * shared_alloc = cudaMalloc + cudaIpcGetMemHandle (handle: 64 bytes, sent to the peers by the host layer);
  * shared_open  = cudaIpcOpenMemHandle in the CALLER's device context (the peer's buffer becomes addressable from

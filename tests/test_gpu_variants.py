@@ -205,6 +205,49 @@ def test_stepwise_cholesky_equals_the_fused_solve(env, n, panel_tiles):
     assert lib.vb200_chol_panel_range(n, T, 1, ctypes.byref(off), ctypes.byref(cnt)) != 0
 
 
+def test_multi_range_update_is_bit_identical(env):
+    """vb200_chol_update_ranges: one DMMA launch over several strided block-column ranges (the panels ONE rank owns
+    in the panel-cyclic factorisation) against one vb200_chol_update per panel.  Same tiles, operands and order."""
+    import ctypes
+
+    vb, kernels, lib = env
+    n, pt = 4300, 3
+    e, nn, d = sample(n, seed=19)
+    system = kernels.GramSystem(n).accumulate(0, e, nn, d, None, e, nn, 1e-5)
+    gram = system.gram.clone()
+    T = (n + 127) // 128
+    panels = [(k0, min(pt, T - k0)) for k0 in range(0, T, pt)]
+    forces = {}
+    for mode in ("per_panel", "ranges"):
+        system.gram.copy_(gram)
+        ptr = system.gram.data_ptr()
+        assert lib.vb200_chol_begin(ptr, system.stats.data_ptr(), n, n, 1e-3) == 0
+        for p, (k0, w) in enumerate(panels):
+            assert lib.vb200_chol_panel(ptr, n, k0, w) == 0
+            later = panels[p + 1:]
+            if mode == "per_panel":
+                for q0, qw in later:
+                    assert lib.vb200_chol_update(ptr, n, k0, w, q0, q0 + qw) == 0
+            else:
+                for phase in (0, 1, 2):  # three "ranks", each with its strided share of the later panels
+                    mine = [(q0, q0 + qw) for q, (q0, qw) in enumerate(later) if q % 3 == phase]
+                    lo = (ctypes.c_int32 * len(mine))(*[a for a, _ in mine])
+                    hi = (ctypes.c_int32 * len(mine))(*[b for _, b in mine])
+                    assert lib.vb200_chol_update_ranges(ptr, n, k0, w, len(mine), lo, hi) == 0
+        out = np.empty(n)
+        info = vb._cabi.FitInfo()
+        assert lib.vb200_chol_finish(ptr, n, out.ctypes.data, ctypes.byref(info)) == 0
+        forces[mode] = out
+    np.testing.assert_array_equal(forces["ranges"], forces["per_panel"])
+    # overlapping or unsorted ranges are refused
+    system.gram.copy_(gram)
+    assert lib.vb200_chol_begin(system.gram.data_ptr(), system.stats.data_ptr(), n, n, 1e-3) == 0
+    lo, hi = (ctypes.c_int32 * 2)(6, 4), (ctypes.c_int32 * 2)(9, 7)
+    assert lib.vb200_chol_update_ranges(system.gram.data_ptr(), n, 0, 3, 2, lo, hi) != 0
+    out = np.empty(n)
+    lib.vb200_chol_finish(system.gram.data_ptr(), n, out.ctypes.data, None)
+
+
 @pytest.mark.parametrize("m,panel,min_rows", [(2500, 2, 4), (14_000, 8, 96)])
 def test_lookahead_cholesky_is_bit_identical(env, m, panel, min_rows):
     """Single-GPU look-ahead: panel p+1 is factored on a few SMs beside the trailing update of panel p (two grids

@@ -52,19 +52,21 @@ for n in sizes:
         system.gram.copy_(keep)
         res["replicated_s"], forces["replicated"] = timed(lambda: system.solve(n, damping))
         res["replicated_factor_ms"] = system.info.factor_ms
-        for mode in ("serial", "lookahead", "peer"):
-            vb.dist.set_panel_pipeline(mode)
+        for mode in ("serial", "lookahead", "peer", "peer_per_panel_updates"):
+            vb.dist.set_panel_pipeline(mode.split("_")[0])
+            vb.dist.set_merged_updates(mode != "peer_per_panel_updates")
             system.info = vb._cabi.FitInfo()
             system.gram.copy_(keep)
-            phases = {}
-            res[mode + "_s"], forces[mode] = timed(lambda: system.solve_distributed(n, damping, phase_times=phases))
-            res[mode + "_rank0_phase_ms"] = {k: round(v, 2) for k, v in phases.items()}
+            res[mode + "_s"], forces[mode] = timed(lambda: system.solve_distributed(n, damping))
             res[mode + "_factor_ms"] = system.info.factor_ms
-            # the same without per-phase events (they add host work between launches)
-            system.info = vb._cabi.FitInfo()
-            system.gram.copy_(keep)
-            res[mode + "_nomarks_s"], _ = timed(lambda: system.solve_distributed(n, damping))
-            res[mode + "_nomarks_factor_ms"] = system.info.factor_ms
+            if mode == "peer":  # per-phase device times of rank 0 (the marks add host work between launches)
+                phases = {}
+                system.info = vb._cabi.FitInfo()
+                system.gram.copy_(keep)
+                res[mode + "_marked_s"], _ = timed(lambda: system.solve_distributed(n, damping, phase_times=phases))
+                res[mode + "_rank0_phase_ms"] = {k: round(v, 2) for k, v in phases.items()}
+        vb.dist.set_merged_updates(True)
+        vb.dist.set_panel_pipeline("peer")
     mine = torch.from_numpy(forces["peer"]).cuda()
     lo, hi = mine.clone(), mine.clone()
     td.all_reduce(lo, op=td.ReduceOp.MIN); td.all_reduce(hi, op=td.ReduceOp.MAX)
@@ -73,7 +75,9 @@ for n in sizes:
     res["peer_vs_serial_bit_identical"] = bool(np.array_equal(forces["peer"], forces["serial"]))
     res["distributed_vs_replicated_bit_identical"] = bool(np.array_equal(forces["serial"], forces["replicated"]))
     res["cond_est"], res["backward_err"] = system.info.cond_est, system.info.backward_err
+    res["per_panel_updates_vs_merged_bit_identical"] = bool(np.array_equal(forces["peer_per_panel_updates"], forces["peer"]))
     ok = ok and res["ranks_agree"] and res["lookahead_vs_serial_bit_identical"] and res["peer_vs_serial_bit_identical"]
+    ok = ok and res["per_panel_updates_vs_merged_bit_identical"]
     if rank == 0:
         print(json.dumps(res), flush=True)
     del system, keep

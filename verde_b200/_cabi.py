@@ -86,6 +86,7 @@ SIGNATURES = {
     "vb200_chol_panel_range": (ctypes.c_int, [i64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
     "vb200_chol_panel": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_int32, ctypes.c_int32]),
     "vb200_chol_update": (ctypes.c_int, [ctypes.c_void_p, i64] + [ctypes.c_int32] * 4),
+    "vb200_chol_update_ranges": (ctypes.c_int, [ctypes.c_void_p, i64] + [ctypes.c_int32] * 3 + [ctypes.c_void_p] * 2),
     "vb200_shared_alloc": (ctypes.c_int, [i64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "vb200_shared_free": (ctypes.c_int, [ctypes.c_void_p]),
     "vb200_shared_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),

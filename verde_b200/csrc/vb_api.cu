@@ -184,7 +184,8 @@ cudaError_t timed_gemm(const VbGemmParams &p, cudaStream_t st)
     if (e != cudaSuccess) return e;
     e = vb_launch_gemm(p, st);
     cudaEventRecord(s.b, st);
-    const double flops = 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi) *
+    VbGemmParams counted = p;
+    const double flops = 2.0 * VB_TILE * VB_TILE * VB_TILE * (double)p.nk * (double)vb_gemm_launch_tiles(counted) *
                          (double)(p.batch > 1 ? p.batch : 1);
     if (p.untimed == 2) {
         g_prof.shared.push_back(s);
@@ -1061,6 +1062,21 @@ int vb200_chol_update(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, in
     if (!chol_dev || k0 < 0 || pw < 1 || pw > VB_MAX_KCHUNKS || k0 + pw > T || j_lo < k0 + pw || j_hi > T)
         return fail(VB200_E_BADARG, "bad update range");
     CU(vb_chol_trailing_update(chol_dev, T, k0, pw, j_lo, j_hi, 0));
+    return 0;
+}
+
+int vb200_chol_update_ranges(double *chol_dev, int64_t cols, int32_t k0, int32_t pw, int32_t n_ranges,
+                             const int32_t *j_lo, const int32_t *j_hi)
+{
+    const int T = (int)((cols + VB_TILE - 1) / VB_TILE);
+    if (!g_step.open || g_step.cols != cols) return fail(VB200_E_BADARG, "vb200_chol_begin was not called for this system");
+    if (!chol_dev || k0 < 0 || pw < 1 || pw > VB_MAX_KCHUNKS || k0 + pw > T || n_ranges < 0 || (n_ranges > 0 && (!j_lo || !j_hi)))
+        return fail(VB200_E_BADARG, "bad update ranges");
+    for (int r = 0; r < n_ranges; ++r)
+        if (j_lo[r] < k0 + pw || j_hi[r] > T || j_hi[r] < j_lo[r] || (r > 0 && j_lo[r] < j_hi[r - 1]))
+            return fail(VB200_E_BADARG, "update ranges must be ascending, disjoint and right of the panel");
+    if (n_ranges == 0) return 0;
+    CU(vb_chol_trailing_update_ranges(chol_dev, T, k0, pw, n_ranges, j_lo, j_hi, 0));
     return 0;
 }
 

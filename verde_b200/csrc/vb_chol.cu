@@ -577,6 +577,36 @@ cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, 
     return trailing_update_ex(L, T, k0, pw, j_lo, j_hi, stream, batch, stride, nullptr, 0, 0);
 }
 
+cudaError_t vb_chol_trailing_update_ranges(double *L, int T, int k0, int pw, int nranges, const int *j_lo,
+                                           const int *j_hi, cudaStream_t stream)
+{
+    for (int r0 = 0; r0 < nranges; r0 += VB_MAX_RANGES) {
+        VbGemmParams p = {};
+        p.a_base = p.b_base = L;
+        p.c_base = L;
+        p.T = T;
+        p.nk = pw;
+        for (int kk = 0; kk < pw; ++kk) p.a_chunk_off[kk] = p.b_chunk_off[kk] = col_base(k0 + kk, T);
+        p.alpha = -1.0;
+        p.accumulate = 1;
+        p.batch = 1;
+        for (int r = r0; r < nranges && r < r0 + VB_MAX_RANGES; ++r) {
+            const int lo = j_lo[r] < k0 + pw ? k0 + pw : j_lo[r];
+            const int hi = j_hi[r] > T ? T : j_hi[r];
+            if (lo >= hi) continue;
+            p.range_lo[p.nranges] = lo;
+            p.range_hi[p.nranges] = hi;
+            ++p.nranges;
+        }
+        if (p.nranges == 0) continue;
+        p.j_lo = p.range_lo[0];
+        p.j_hi = p.range_hi[p.nranges - 1];
+        cudaError_t e = vb_gemm_dispatch(p, stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // Multi-GPU panel exchange over peer memory: the owner of a panel PUSHES it into every peer's copy of the matrix
 // with copy engines (no SM, no collective) and then writes the fit's epoch into that peer's per-panel flag word.
 // The receiver's stream parks on the flag with this one-thread kernel (system-scope acquire: the writer is another

@@ -81,6 +81,18 @@ __device__ __forceinline__ void decode_tile(long long t, int T, int j_lo, int j_
     }
 }
 
+// tile id of a launch that may cover several block-column ranges (VbGemmParams::nranges)
+__device__ __forceinline__ void decode_tile_ranges(const VbGemmParams &p, long long t, int &bi, int &bj)
+{
+    if (p.nranges > 0) {
+        int r = 0;
+        while (r + 1 < p.nranges && t >= p.range_first[r + 1]) ++r;
+        decode_tile(t - p.range_first[r], p.T, p.range_lo[r], p.range_hi[r], p.strip, bi, bj);
+    } else {
+        decode_tile(t, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+    }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1) vb_gemm_kernel(const VbGemmParams p)
 {
     extern __shared__ __align__(16) double smem[];
@@ -516,7 +528,7 @@ vb_gemm_dynamic_kernel(const VbGemmParams p, long long ntiles, unsigned long lon
             bool diag = false;
             if (!done) {
                 const long long mat = t / ntiles;
-                decode_tile(t - mat * ntiles, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+                decode_tile_ranges(p, t - mat * ntiles, bi, bj);
                 moff = mat * p.batch_stride;
                 diag = (bi == bj) && (p.a_base == p.b_base);
             }
@@ -561,7 +573,7 @@ vb_gemm_dynamic_kernel(const VbGemmParams p, long long ntiles, unsigned long lon
             if (t < 0) break;
             int bi, bj;
             const long long mat = t / ntiles;
-            decode_tile(t - mat * ntiles, p.T, p.j_lo, p.j_hi, p.strip, bi, bj);
+            decode_tile_ranges(p, t - mat * ntiles, bi, bj);
             const bool diag = (bi == bj) && (p.a_base == p.b_base);
             double acc[MI][4][2];
 #pragma unroll
@@ -790,12 +802,35 @@ long long vb_gemm_num_tiles(int T, int j_lo, int j_hi)
     return total;
 }
 
+long long vb_gemm_launch_tiles(VbGemmParams &p)
+{
+    if (p.nranges <= 0) return vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
+    long long total = 0;
+    for (int r = 0; r < p.nranges; ++r) {
+        p.range_first[r] = total;
+        total += vb_gemm_num_tiles(p.T, p.range_lo[r], p.range_hi[r]);
+    }
+    return total;
+}
+
 cudaError_t vb_launch_gemm(const VbGemmParams &p_in, cudaStream_t stream)
 {
+    if (p_in.nranges > 0 && vb_gemm_variant != 4) {
+        // only the dynamic kernel walks several ranges in one launch
+        for (int r = 0; r < p_in.nranges; ++r) {
+            VbGemmParams q = p_in;
+            q.nranges = 0;
+            q.j_lo = p_in.range_lo[r];
+            q.j_hi = p_in.range_hi[r];
+            cudaError_t er = vb_launch_gemm(q, stream);
+            if (er != cudaSuccess) return er;
+        }
+        return cudaSuccess;
+    }
     VbGemmParams p = p_in;
     p.strip = vb_gemm_strip < 1 ? 1 : vb_gemm_strip;
     if (p.nk <= 0 || p.nk > VB_MAX_KCHUNKS) return cudaErrorInvalidValue;
-    const long long tiles = vb_gemm_num_tiles(p.T, p.j_lo, p.j_hi);
+    const long long tiles = vb_gemm_launch_tiles(p);
     if (tiles <= 0) return cudaSuccess;
     cudaError_t e;
     if (p.batch > 1 && vb_gemm_variant != 3 && vb_gemm_variant != 4) {

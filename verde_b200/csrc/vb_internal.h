@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #define VB_MAX_KCHUNKS 16
+#define VB_MAX_RANGES 32
 
 // One launch of the DMMA tile kernel:
 //   for every lower-triangle tile (bi, bj), j_lo <= bj < j_hi, bj <= bi < T:
@@ -32,11 +33,19 @@ struct VbGemmParams {
     // factorisation join an update that is already running.  grid_limit > 0 caps the persistent grid.
     unsigned long long *queue;
     int grid_limit;
+    // nranges > 0 (dynamic kernel only): the launch covers the block-column ranges [range_lo[r], range_hi[r]) instead of
+    // [j_lo, j_hi) -- the panels ONE rank owns in the panel-cyclic multi-GPU factorisation are strided, and one launch
+    // over all of them has one tail instead of one per panel.  range_first[r] = tiles before range r.
+    int nranges;
+    int range_lo[VB_MAX_RANGES], range_hi[VB_MAX_RANGES];
+    long long range_first[VB_MAX_RANGES];
     int untimed;  // 1: keep this launch out of the CUDA-event profile (the second grid of a shared queue);
                   // 2: time it, but as a launch that shares the GPU with a panel factorisation (shared_gemm_*)
 };
 
 long long vb_gemm_num_tiles(int T, int j_lo, int j_hi);
+// tiles of one matrix of a launch (all ranges); fills range_first when the launch has ranges
+long long vb_gemm_launch_tiles(VbGemmParams &p);
 cudaError_t vb_launch_gemm(const VbGemmParams &p, cudaStream_t stream);
 // a zeroed tile-queue counter (zeroed in `stream` order) for launches that share one queue
 cudaError_t vb_gemm_new_queue(unsigned long long **queue, cudaStream_t stream);
@@ -131,6 +140,9 @@ cudaError_t vb_chol_factor_panel(double *L, int T, int k0, int pw, int *d_info, 
                                  int batch = 1, long long stride = 0);
 cudaError_t vb_chol_trailing_update(double *L, int T, int k0, int pw, int j_lo, int j_hi,
                                     cudaStream_t stream, int batch = 1, long long stride = 0);
+// the same for several block-column ranges in ONE launch of the dynamic kernel (the panels a rank owns)
+cudaError_t vb_chol_trailing_update_ranges(double *L, int T, int k0, int pw, int nranges, const int *j_lo,
+                                           const int *j_hi, cudaStream_t stream);
 // park `stream` until *flag >= value (written by a peer GPU); a timeout stores -1 in *d_info
 cudaError_t vb_chol_wait_flag(const long long *flag, long long value, int *d_info, cudaStream_t stream);
 // offset (doubles) of the diagonal tile of block column c: columns [c0, c1) occupy the contiguous

@@ -149,6 +149,24 @@ def panel_pipeline():
     return _PANEL_PIPELINE
 
 
+_MERGED_UPDATES = True
+
+
+def set_merged_updates(flag):
+    """
+    Look-ahead / peer schedules: apply a factored panel to ALL the later panels a rank owns with one launch of the
+    DMMA kernel (``vb200_chol_update_ranges``; default) instead of one launch per owned panel.  Same tiles, same
+    operands, same order per tile -> bit-identical factors; what changes is one tail per outer panel instead of one
+    per (outer panel, owned panel) pair.
+    """
+    global _MERGED_UPDATES
+    _MERGED_UPDATES = bool(flag)
+
+
+def merged_updates():
+    return _MERGED_UPDATES
+
+
 def next_epoch():
     "A number that grows with every collective call of the panel-cyclic factorisation (identical on every rank)."
     _EPOCH[0] += 1

@@ -336,6 +336,22 @@ class GramSystem:
         # taking part in every collective, and all ranks raise together after ``agree_on_status``.
         status = 0
         torch = self._torch
+
+        def update_owned(k0, width, panels):
+            "apply panel [k0, k0 + width) to the later panels this rank owns: ONE launch over all their block columns"
+            owned = [(q0, q0 + qwidth) for q0, qwidth, qowner in panels if qowner == rank]
+            if not owned:
+                return 0
+            if not dist.merged_updates():
+                for lo, hi in owned:
+                    rc = lib.vb200_chol_update(gram_ptr, cols, k0, width, lo, hi)
+                    if rc != 0:
+                        return rc
+                return 0
+            los = (ctypes.c_int32 * len(owned))(*[lo for lo, _ in owned])
+            his = (ctypes.c_int32 * len(owned))(*[hi for _, hi in owned])
+            return lib.vb200_chol_update_ranges(gram_ptr, cols, k0, width, len(owned), los, his)
+
         pipeline = dist.panel_pipeline() if len(schedule) > 1 else "serial"
         if pipeline == "peer" and self._shared is None:
             pipeline = "lookahead"  # this matrix was not allocated for the peer exchange
@@ -392,9 +408,8 @@ class GramSystem:
                     ready.record(main)
                     later = later[1:]
                     mark("panel")
-                for q0, qwidth, qowner in later:
-                    if qowner == rank and status == 0:
-                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                if status == 0:
+                    status = update_owned(k0, width, later)
                 mark("update")
             done = torch.cuda.Event()
             done.record(comm)
@@ -433,9 +448,8 @@ class GramSystem:
                     ready.record(main)
                     later = later[1:]
                     mark("panel")
-                for q0, qwidth, qowner in later:
-                    if qowner == rank and status == 0:
-                        status = lib.vb200_chol_update(gram_ptr, cols, k0, width, q0, q0 + qwidth)
+                if status == 0:
+                    status = update_owned(k0, width, later)
                 mark("update")
             main.wait_event(last)
         else:
