@@ -379,6 +379,20 @@ def multi_gpu_parity(vb, world):
         spd = vb.Spline(damping=1e-4).fit((e, n), d, weights=w)
         vb.dist.set_cholesky("auto")
         out["distributed_vs_replicated_cholesky_force"] = rel(spd.force_, sp.force_)
+        # Vector([Spline, Spline]) under sharding: one row-sharded Gram matrix + one factor for both components,
+        # one point-sharded Green's evaluation for both predictions; component 0 against the reference golden,
+        # component 1 against its own (sharded) independent fit
+        d2 = np.cos(e / 700.0) * 300.0 + n * 0.05
+        vec = vb.Vector([vb.Spline(damping=1e-4), vb.Spline(damping=1e-4)]).fit((e, n), (d, d2), weights=(w, w))
+        alone = vb.Spline(damping=1e-4).fit((e, n), d2, weights=w)
+        grid = (g["grid_east"], g["grid_north"])
+        pred = vec.predict(grid)
+        out["vector_of_splines_shared_factor"] = {
+            "component0_force_vs_golden": rel(vec.components[0].force_, g["force_d1em4_w"]),
+            "component1_force_vs_independent_fit": rel(vec.components[1].force_, alone.force_),
+            "component0_grid_vs_golden": float(np.max(np.abs(pred[0] - g["grid_d1em4_w"])) / np.ptp(d)),
+            "component1_grid_vs_independent_fit": float(np.max(np.abs(pred[1] - alone.predict(grid))) / np.ptp(d2)),
+            "shared": bool(vec._splines_share_forces())}
         v = np.load(os.path.join(golden, "vector_small.npz"))
         vs = vb.VectorSpline2D(damping=1e-3).fit((v["east"], v["north"]), (v["data_east"], v["data_north"]))
         out["vector_small_force"] = rel(vs.force_, v["force_d1em3"])
@@ -427,7 +441,10 @@ def multi_gpu_parity(vb, world):
         out["cfg5_2k"] = {"scores_max_diff_by_damping": {str(float(x)): float(diff[:, k].max()) for k, x in enumerate(g5["dampings"])},
                           "best_matches": bool((cv.mindist_, cv.damping_) == (float(g5["best_mindist"]), float(g5["best_damping"]))),
                           "jobs_this_rank": int(cv.sweep_info_["jobs"])}
+    vos = out["vector_of_splines_shared_factor"]
     ok = (out["spline_small_force"] < 1e-5 and out["spline_small_grid"] < 1e-6 and out["vector_small_force"] < 1e-6
+          and vos["component0_force_vs_golden"] < 1e-5 and vos["component1_force_vs_independent_fit"] < 1e-5
+          and vos["component0_grid_vs_golden"] < 1e-6 and vos["component1_grid_vs_independent_fit"] < 1e-7
           and out["distributed_vs_replicated_cholesky_force"] < 1e-9 and out["cv_small_scores"] < 1e-7
           and out["cv_small_best_matches"] and out["cfg3_40k"]["force"] <= out["cfg3_40k"]["force_tol"]
           and out["cfg3_40k"]["grid_over_range"] < 1e-6 and out["cfg4_3k"]["force"] <= out["cfg4_3k"]["force_tol"]

@@ -214,6 +214,10 @@ int vb200_shared_close(void *ptr);
  * rank's matrix with a copy engine, is >= epoch.  Asynchronous; a panel that does not arrive within ~10 s makes
  * vb200_chol_finish return VB200_E_CUDA instead of hanging. */
 int vb200_chol_wait_panel(const int64_t *flag_dev, int64_t epoch);
+/* the same wait on a stream of the caller (cudaStream_t; NULL = the library stream): an owner parks its copy stream
+ * on a peer's "ready" word before the first push of a factorisation, so that no panel can land in a matrix whose
+ * scaling pass (vb200_chol_begin) is still running */
+int vb200_stream_wait_flag(const int64_t *flag_dev, int64_t epoch, void *stream);
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) for the pushes above: dst is a peer GPU's memory mapped
  * into this process (CUDA IPC), stream a cudaStream_t of the caller (NULL = the library stream).  Asynchronous. */
 int vb200_peer_copy_async(void *dst, const void *src, int64_t bytes, void *stream);

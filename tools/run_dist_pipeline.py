@@ -67,6 +67,30 @@ for n in sizes:
                 res[mode + "_rank0_phase_ms"] = {k: round(v, 2) for k, v in phases.items()}
         vb.dist.set_merged_updates(True)
         vb.dist.set_panel_pipeline("peer")
+    # Skew stress: back-to-back fits WITHOUT barriers, odd/even ranks delayed in turn by ~50 ms of device time before
+    # the factorisation starts (a pushed panel must never land in a matrix whose scaling pass is still running).
+    skew_ok = True
+    for rep in range(6 if os.environ.get("VB_SKEW_WITHOUT_HANDSHAKE") else 4):
+        vb.dist._READY_HANDSHAKE = rep < 4  # reps 4, 5 (opt-in): the race the handshake closes, made likely by the skew
+        system.info = vb._cabi.FitInfo()
+        system.gram.copy_(keep)
+        if (rank + rep) % 2:
+            torch.cuda._sleep(100_000_000)
+        try:
+            got = system.solve_distributed(n, damping)
+            same = bool(np.array_equal(got, forces["serial"]))
+        except Exception as exc:  # noqa: BLE001
+            same = False
+            res["skew_error_rep%d" % rep] = repr(exc)[:200]
+        if rep < 4:
+            skew_ok = skew_ok and same
+        else:
+            res["without_handshake_rep%d_bit_identical_on_rank0" % rep] = same
+    vb.dist._READY_HANDSHAKE = True
+    flag = torch.tensor([1.0 if skew_ok else 0.0], device="cuda")
+    td.all_reduce(flag, op=td.ReduceOp.MIN)
+    res["skewed_back_to_back_fits_bit_identical"] = bool(flag.item() == 1.0)
+    ok = ok and res["skewed_back_to_back_fits_bit_identical"]
     mine = torch.from_numpy(forces["peer"]).cuda()
     lo, hi = mine.clone(), mine.clone()
     td.all_reduce(lo, op=td.ReduceOp.MIN); td.all_reduce(hi, op=td.ReduceOp.MAX)

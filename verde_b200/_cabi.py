@@ -92,6 +92,7 @@ SIGNATURES = {
     "vb200_shared_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "vb200_shared_close": (ctypes.c_int, [ctypes.c_void_p]),
     "vb200_chol_wait_panel": (ctypes.c_int, [ctypes.c_void_p, i64]),
+    "vb200_stream_wait_flag": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_void_p]),
     "vb200_peer_copy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, i64, ctypes.c_void_p]),
     "vb200_chol_finish": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_block_split": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(i64)]),

@@ -53,7 +53,7 @@ class Vector(BaseGridder):
         the right-hand sides differ, so one Gram accumulation + one Cholesky serves them all.
         """
         comps = self.components
-        if not isinstance(data, tuple) or len(comps) < 2 or len(comps) != len(data) or dist.sharding_active():
+        if not isinstance(data, tuple) or len(comps) < 2 or len(comps) != len(data):
             return False
         first = comps[0]
         if any(type(c) is not Spline for c in comps) or first.damping is None:
@@ -76,16 +76,38 @@ class Vector(BaseGridder):
         force_east, force_north = n_1d_arrays(force_coords, n=2)
         w = weights[0]
         kernels._warn_underdetermined(east.size, force_east.size)
-        system = kernels.GramSystem(force_east.size)
-        system.accumulate(0, east, north, data[0], w, force_east, force_north, first.mindist)
+        east, north = (np.ascontiguousarray(c, dtype=np.float64) for c in (east, north))
+        # Under sharding (one process per GPU) a rank accumulates its contiguous row range, the Gram matrix and the
+        # right-hand sides are all-reduced, and every rank factors the (identical) reduced matrix once and solves
+        # every component against it: all ranks end with the same forces.
+        sharded = dist.sharding_active()
+        a, b = dist.shard_bounds(east.size) if sharded else (0, east.size)
+        w_rows = None if w is None else np.ravel(w)[a:b]
+        system, failure = None, None
+        try:
+            system = kernels.GramSystem(force_east.size, peer_exchange=False)
+            system.accumulate(0, east[a:b], north[a:b], np.ravel(data[0])[a:b], w_rows, force_east, force_north,
+                              first.mindist)
+        except (MemoryError, ValueError, kernels._cabi.EngineError) as exc:
+            failure = exc
+        if sharded:
+            lowest, _ = dist.agree_on_status(-1 if failure is not None else 0)
+            if failure is None and lowest < 0:
+                failure = kernels._cabi.EngineError("Vector: the shared Gram accumulation failed on another rank")
+        if failure is not None:
+            raise failure
+        if sharded:
+            system.allreduce()
         system.factor(east.size, first.damping)
         region = get_region(coordinates[:2])
         for k, (estimator, data_comp) in enumerate(zip(self.components, data)):
             if k == 0:
                 rhs = system.rhs()
             else:
-                v = np.ravel(data_comp) if w is None else np.ravel(w) * np.ravel(data_comp)
-                rhs = kernels.jacobian_transpose_apply(east, north, force_east, force_north, first.mindist, v)
+                v = np.ravel(data_comp)[a:b] if w is None else w_rows * np.ravel(data_comp)[a:b]
+                rhs = kernels.jacobian_transpose_apply(east[a:b], north[a:b], force_east, force_north, first.mindist, v)
+                if sharded:
+                    rhs = dist.allreduce_sum_numpy(rhs)
             estimator.force_ = system.solve_rhs(rhs)
             estimator.region_ = region
             estimator.force_coords_ = (force_coords if first.force_coords is not None
@@ -95,7 +117,7 @@ class Vector(BaseGridder):
     def _splines_share_forces(self):
         "Fitted Splines on the same force positions and mindist: one Green's evaluation serves every component."
         comps = self.components
-        if len(comps) < 2 or dist.sharding_active() or any(type(c) is not Spline for c in comps):
+        if len(comps) < 2 or any(type(c) is not Spline for c in comps):
             return False
         if any(not hasattr(c, "force_") or c.mindist != comps[0].mindist for c in comps):
             return False
@@ -115,8 +137,11 @@ class Vector(BaseGridder):
             east, north = (np.ravel(c) for c in np.broadcast_arrays(*coordinates[:2]))
         force_east, force_north = n_1d_arrays(self.components[0].force_coords_, n=2)
         forces = np.stack([np.asarray(c.force_, dtype=np.float64) for c in self.components])
-        out = np.empty((forces.shape[0], east.size), dtype=np.float64)
-        kernels.predict_multi_b200(east, north, force_east, force_north, self.components[0].mindist, forces, out)
+        if dist.sharding_active():
+            out = kernels.predict_multi_sharded(east, north, force_east, force_north, self.components[0].mindist, forces)
+        else:
+            out = np.empty((forces.shape[0], east.size), dtype=np.float64)
+            kernels.predict_multi_b200(east, north, force_east, force_north, self.components[0].mindist, forces, out)
         dtype = east.dtype if np.issubdtype(east.dtype, np.floating) else np.float64
         return tuple(out[k].astype(dtype, copy=False).reshape(shape) for k in range(forces.shape[0]))
 

@@ -1138,6 +1138,16 @@ int vb200_chol_wait_panel(const int64_t *flag_dev, int64_t epoch)
     return 0;
 }
 
+int vb200_stream_wait_flag(const int64_t *flag_dev, int64_t epoch, void *stream)
+{
+    if (!flag_dev || !is_device_ptr(flag_dev)) return fail(VB200_E_BADARG, "the flag must be device memory");
+    int *d_info;
+    CU(ws_get("info", sizeof(int), (void **)&d_info));
+    CU(vb_chol_wait_flag(reinterpret_cast<const long long *>(flag_dev), (long long)epoch, d_info,
+                         static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int vb200_chol_finish(const double *chol_dev, int64_t cols, double *out_params, vb200_fit_info *info)
 {
     if (!g_step.open || g_step.cols != cols) return fail(VB200_E_BADARG, "vb200_chol_begin was not called for this system");

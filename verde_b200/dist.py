@@ -150,6 +150,8 @@ def panel_pipeline():
 
 
 _MERGED_UPDATES = True
+_READY_HANDSHAKE = True  # peer exchange: wait for every peer's "matrix in place" word before the first push (tools/
+                         # run_dist_pipeline.py switches it off once to show that its skew test catches the race)
 
 
 def set_merged_updates(flag):

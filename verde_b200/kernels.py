@@ -360,7 +360,8 @@ class GramSystem:
             # by the owner of panel p (the fit's epoch) after the panel itself has landed in this rank's matrix.
             if self._window is None:
                 self._window = dist.PeerWindow(self._shared)
-            if len(schedule) > self._flags.numel():
+            ready_base = self._flags.numel() - 1024  # flags[ready_base + r]: rank r's matrix is ready to receive
+            if len(schedule) > ready_base or size > 1024:
                 raise ValueError("too many outer panels for the peer exchange ({})".format(len(schedule)))
             epoch = dist.next_epoch()
             main = torch.cuda.current_stream()
@@ -372,6 +373,17 @@ class GramSystem:
             flag_ptr = self._flags.data_ptr()
             comm_handle = ctypes.c_void_p(comm.cuda_stream)
             my_gram, epoch_ptr = self.gram.data_ptr(), self._epoch_src.data_ptr()
+            # Ready handshake.  vb200_chol_begin rewrites the WHOLE matrix in place (scaling + damping); a panel
+            # pushed by a faster peer before that pass has finished here would be scaled again or overwritten.  So
+            # every rank tells its peers "my matrix is in place" (ordered after chol_begin through `seeded`), and
+            # parks its copy stream until every peer has said the same, before its first push.
+            peers = [r for r in range(size) if r != rank] if dist._READY_HANDSHAKE else []
+            for r in peers:
+                lib.vb200_peer_copy_async(ctypes.c_void_p(self._window.ptr(r, "flags") + 8 * (ready_base + rank)),
+                                          ctypes.c_void_p(epoch_ptr), 8, comm_handle)
+            for r in peers:
+                rc = lib.vb200_stream_wait_flag(ctypes.c_void_p(flag_ptr + 8 * (ready_base + r)), epoch, comm_handle)
+                status = status or rc
 
             def push(p, k0, width, ready):
                 "owner: copy panel p and then its flag into every peer, the owner of panel p+1 first"
@@ -629,6 +641,42 @@ def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindi
     if system.info.lambda_max > 0:  # diagnostics on: backward error of the sharded system
         system.backward_error(kind, e[a:b], n[a:b], d, w, fe, fn, mindist, poisson, force, rows, damping)
     return force
+
+
+def predict_multi_sharded(east, north, force_east, force_north, mindist, forces):
+    """
+    ``predict_multi_b200`` with the points sharded over the ranks: each rank evaluates its contiguous slice for all
+    components at once (one Green's evaluation per pair), one gather per component; returns (components, n) float64,
+    identical on every rank.
+    """
+    from . import dist
+
+    e, n = _cabi.f64(east), _cabi.f64(north)
+    f = np.ascontiguousarray(forces, dtype=np.float64)
+    comps = f.shape[0]
+    if dist.backend() == "nccl":
+        import torch
+
+        lib = _cabi.require_device()
+        fe, fn = _cabi.f64(force_east), _cabi.f64(force_north)
+
+        def compute(views, a, b):
+            if b <= a:
+                return
+            # the kernel writes a contiguous (components, b - a) matrix; the gather buffer keeps one slot per rank
+            local = torch.empty((comps, b - a), dtype=torch.float64, device=views[0].device)
+            _cabi.check(lib.vb200_predict_multi(_cabi.ptr(e[a:b]), _cabi.ptr(n[a:b]), b - a, _cabi.ptr(fe), _cabi.ptr(fn),
+                                                _cabi.ptr(f), fe.size, comps, float(mindist), _cabi.ptr(local)),
+                        "sharded predict_multi")
+            for c in range(comps):
+                views[c].copy_(local[c])
+
+        return np.stack(dist.gather_device_shards(compute, e.size, components=comps))
+    a, b = dist.shard_bounds(e.size)
+    local = np.empty((comps, b - a), dtype=np.float64)
+    if b > a:
+        predict_multi_b200(e[a:b], n[a:b], force_east, force_north, mindist, f, local)
+    return np.stack([dist.allgather_concat(local[c], e.size) for c in range(comps)])
 
 
 def predict_sharded(east, north, force_east, force_north, mindist, forces, poisson=None):
