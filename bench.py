@@ -16,6 +16,9 @@ Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
           forces at the 50 151 BlockReduce(np.mean, shape=(224, 224)) block centres of
           the 400 000 points (computed on the device), grid 2000 x (2000 * N) points
           sharded across ranks.  N = 8 is configs[2]'s own 400k x 50k system.
+          Damping = 1e-6 * sum(weights) / 50 000 (configs[1]'s relative damping, see
+          config3_damping: cond(A) <= 4.6e15 at every N; at a flat 1e-6 the weighted
+          200k- and 400k-row systems are not positive definite in FP64).
           Outside the timed region every rank also runs the sharded estimator API
           (Spline, VectorSpline2D, SplineCV) on the reference's golden cases and rank 0
           reports the gaps in "parity".
@@ -110,6 +113,19 @@ def config3_points():
     north = rng.uniform(REGION[2], REGION[3], CONFIG3_POINTS)
     weights = np.random.RandomState(1).uniform(0.1, 10, CONFIG3_POINTS)
     return east, north, checkerboard(east, north), weights
+
+
+def config3_damping(n_data):
+    """
+    Damping of the N > 1 workload.  BASELINE configs[2] names no damping, and configs[1]'s 1e-6 does not carry over:
+    lambda_max(A) = 9.2e4 * sum(w) grows with the rows and their weights, and with the config's weights the 200 000- and
+    400 000-row systems are NOT numerically positive definite in FP64 at 1e-6 (measured: first non-positive pivots 19 829
+    and 4 760, profiles/r02l_config3_conditioning.jsonl; the reference's Ridge would fall back to an SVD solve there).
+    The damping is therefore scaled with the total weight, damping = 1e-6 * sum(w) / 50 000 -- configs[1]'s RELATIVE
+    damping, so that cond(A) <= lambda_max / damping = 4.6e15 at every N, the conditioning configs[1] is quoted at.
+    """
+    weights = np.random.RandomState(1).uniform(0.1, 10, CONFIG3_POINTS)
+    return DAMPING * float(np.sum(weights[:n_data])) / 50_000.0
 
 
 def make_config3_workload(n_data, grid_shape, block_reduce):
@@ -324,13 +340,16 @@ def workload_config(world, n_rank=50_000, m=50_000, grid=2000):
     if world > 1:
         full = (n_rank * world, grid) == (CONFIG3_POINTS, 2000)
         return {
-            "workload": ("{}: Spline(damping=1e-6, mindist=1e-5), the first {} of config 3's 400000 CheckerBoard points "
+            "workload": ("{}: Spline(damping=1e-6*sum(w)/50000, mindist=1e-5), the first {} of config 3's 400000 CheckerBoard points "
                          "(rows sharded over {} ranks), weights RandomState(1).uniform(0.1, 10), {} forces at the "
                          "BlockReduce(mean, shape=(224, 224)) centres of the 400000 points, grid {}x{} sharded".format(
                              "BASELINE configs[2]'s 400k x 50k system" if full else "weak-scaled towards BASELINE configs[2]",
                              n_rank * world, world, m, grid, grid * world)),
             "n_data": n_rank * world, "n_forces": m, "grid_points": grid * grid * world, "weights": True,
-            "damping": DAMPING, "mindist": MINDIST, "parallelism": "rows+grid sharded x{}".format(world),
+            "damping": config3_damping(n_rank * world), "mindist": MINDIST,
+            "damping_rule": "1e-6 * sum(weights) / 50000: configs[1]'s relative damping, cond(A) <= 4.6e15 at every N "
+                            "(at 1e-6 the weighted 200k/400k-row systems are not positive definite in FP64)",
+            "parallelism": "rows+grid sharded x{}".format(world),
             "l2": "inputs larger than L2 (10 GB Gram matrix streamed); no explicit flush",
         }
     base = "BASELINE configs[1]" if (n_rank, m, grid) == (50_000, 50_000, 2000) else "REDUCED-SIZE variant of configs[1]"
@@ -510,6 +529,7 @@ def main():
 
     n_rank = args.size
     n_total = n_rank * world
+    damping = config3_damping(n_total) if world > 1 else DAMPING
     grid_shape = (args.grid, args.grid * world)
     npts_total = grid_shape[0] * grid_shape[1]
     if world > 1:
@@ -560,7 +580,7 @@ def main():
         ev[0].record()
         if world == 1:
             rc = lib.vb200_spline_fit(_cabi.ptr(d_e), _cabi.ptr(d_n), _cabi.ptr(d_d), None, b - a, _cabi.ptr(d_fe),
-                                      _cabi.ptr(d_fn), m, MINDIST, DAMPING, _cabi.ptr(d_force), ctypes.byref(info))
+                                      _cabi.ptr(d_fn), m, MINDIST, damping, _cabi.ptr(d_force), ctypes.byref(info))
             _cabi.check(rc, "bench fit")
         else:
             ctypes.memset(ctypes.byref(info), 0, ctypes.sizeof(info))
@@ -571,14 +591,14 @@ def main():
             system.allreduce()
             if dist_chol:
                 system.info = info
-                system.solve_distributed(n_total, DAMPING, panel_tiles=8, out=d_force)
+                system.solve_distributed(n_total, damping, panel_tiles=8, out=d_force)
             else:
-                rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, DAMPING, 0,
+                rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, damping, 0,
                                           _cabi.ptr(d_force), ctypes.byref(info))
                 _cabi.check(rc, "bench solve")
                 system.info = info
             if info.lambda_max > 0:  # diagnostics on: backward error of the row-sharded system (m doubles all-reduced)
-                system.backward_error(0, d_e, d_n, d_d, d_w, d_fe, d_fn, MINDIST, 0.0, d_force, n_total, DAMPING)
+                system.backward_error(0, d_e, d_n, d_d, d_w, d_fe, d_fn, MINDIST, 0.0, d_force, n_total, damping)
         ev[1].record()
         rc = lib.vb200_predict(_cabi.ptr(d_gx), _cabi.ptr(d_gy), pb - pa, _cabi.ptr(d_fe), _cabi.ptr(d_fn),
                                _cabi.ptr(d_force), m, MINDIST, _cabi.ptr(d_out))
@@ -647,7 +667,7 @@ def main():
         def api_step():
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore", FutureWarning)
-                spline = vb.Spline(damping=DAMPING, mindist=MINDIST, force_coords=force_coords)
+                spline = vb.Spline(damping=damping, mindist=MINDIST, force_coords=force_coords)
             spline.fit((h_e, h_n), h_d, weights=h_w)
             result["grid"] = spline.predict((h_gx, h_gy))
             result["force"] = spline.force_

@@ -67,6 +67,11 @@ for n in sizes:
                 res[mode + "_rank0_phase_ms"] = {k: round(v, 2) for k, v in phases.items()}
         vb.dist.set_merged_updates(True)
         vb.dist.set_panel_pipeline("peer")
+        for pt in [int(v) for v in os.environ.get("VB_PANEL_TILES", "").split(",") if v]:
+            system.info = vb._cabi.FitInfo()
+            system.gram.copy_(keep)
+            res["peer_panel_tiles_%d_s" % pt], _ = timed(lambda: system.solve_distributed(n, damping, panel_tiles=pt))
+            res["peer_panel_tiles_%d_factor_ms" % pt] = system.info.factor_ms
     # Skew stress: back-to-back fits WITHOUT barriers, odd/even ranks delayed in turn by ~50 ms of device time before
     # the factorisation starts (a pushed panel must never land in a matrix whose scaling pass is still running).
     skew_ok = True
