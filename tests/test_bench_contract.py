@@ -79,6 +79,20 @@ def test_reference_arm_uses_all_cores_under_torchrun_environment():
     cfg = line["config"]
     assert line["n_gpus"] == 2 and cfg["n_data"] == 100_000 and cfg["n_forces"] == 50_151 and cfg["weights"] is True
     assert cfg["grid_points"] == 8_000_000
+    # the N > 1 damping follows the total weight (config 2's relative damping), identically in both arms
+    assert abs(cfg["damping"] - bench.config3_damping(100_000)) < 1e-20 and "damping_rule" in cfg
+    assert cfg == bench.workload_config(2, 50_000, 50_151, 2000)
+
+
+def test_config3_damping_keeps_the_relative_damping_of_config_2():
+    import numpy as np
+
+    import bench
+
+    w = np.random.RandomState(1).uniform(0.1, 10, 400_000)
+    for n in (100_000, 200_000, 400_000):
+        np.testing.assert_allclose(bench.config3_damping(n), 1e-6 * w[:n].sum() / 50_000, rtol=1e-14)
+    assert 3.9e-5 < bench.config3_damping(400_000) < 4.2e-5
 
 
 def test_config3_workload_generator():
