@@ -564,7 +564,8 @@ def main():
     d_out = torch.empty(pb - pa, dtype=torch.float64, device=dev)
     system = kernels.GramSystem(m) if world > 1 else None
     vb.dist.set_cholesky(args.cholesky)
-    dist_chol = world > 1 and vb.dist.use_distributed_cholesky((m + 127) // 128, 8, world)
+    panel_tiles = vb.dist.panel_tiles(world)
+    dist_chol = world > 1 and vb.dist.use_distributed_cholesky((m + 127) // 128, panel_tiles, world)
     info = _cabi.FitInfo()
     phase = {}
 
@@ -591,7 +592,7 @@ def main():
             system.allreduce()
             if dist_chol:
                 system.info = info
-                system.solve_distributed(n_total, damping, panel_tiles=8, out=d_force)
+                system.solve_distributed(n_total, damping, panel_tiles=panel_tiles, out=d_force)
             else:
                 rc = lib.vb200_gram_solve(_cabi.ptr(system.gram), _cabi.ptr(system.stats), m, n_total, damping, 0,
                                           _cabi.ptr(d_force), ctypes.byref(info))
@@ -706,8 +707,8 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(world, n_rank, m, args.grid),  # identical to the reference arm's config
         "cholesky": ("single GPU" if world == 1 else
-                     "panel-cyclic over {} ranks, look-ahead, panel exchange: {}".format(
-                         world, {"peer": "copy-engine pushes into peer memory (CUDA IPC over NVLink) + flag words",
+                     "panel-cyclic over {} ranks, outer panels of {} block columns, look-ahead, panel exchange: {}".format(
+                         world, panel_tiles, {"peer": "copy-engine pushes into peer memory (CUDA IPC over NVLink) + flag words",
                                  "lookahead": "ncclBroadcast on a side stream", "serial": "ncclBroadcast"}[vb.dist.panel_pipeline()])
                      if dist_chol else
                      "replicated on every rank"),

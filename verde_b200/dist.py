@@ -109,6 +109,19 @@ def panel_cyclic_schedule(block_rows, panel_tiles, size):
             for p, k0 in enumerate(range(0, block_rows, panel_tiles))]
 
 
+def panel_tiles(size=None):
+    """
+    Outer-panel width (block columns of 128) of the panel-cyclic Cholesky.  The chain *panel arrives -> update the
+    next panel -> factor it -> push it* is serial over the panels and its per-panel cost grows with the width, while
+    per-rank update work shrinks with N: measured at m = 50k (profiles/r02m_dist_pipeline_8gpu_panel_widths.jsonl,
+    r02n_dist_pipeline_4gpu_panel_widths.jsonl) N = 8: 234 / 200 / 189 / 182 ms for widths 12 / 8 / 6 / 4;
+    N = 4: 327 / 325 / 325 / 339 ms for 8 / 6 / 4 / 2.  Identical on every rank.
+    """
+    if size is None:
+        size = world()[1]
+    return 4 if size >= 4 else 8
+
+
 def use_distributed_cholesky(block_rows, panel_tiles, size=None):
     "Decision rule of ``set_cholesky``; identical on every rank (it only depends on sizes)."
     if size is None:

@@ -634,8 +634,8 @@ def fit_sharded(kind, east, north, data, weights, force_east, force_north, mindi
     if lowest < 0:
         raise _cabi.EngineError("row-sharded fit: the Gram accumulation failed on another rank")
     system.allreduce()
-    if dist.use_distributed_cholesky((cols + 127) // 128, 8):
-        force = system.solve_distributed(rows, damping, panel_tiles=8)
+    if dist.use_distributed_cholesky((cols + 127) // 128, dist.panel_tiles()):
+        force = system.solve_distributed(rows, damping, panel_tiles=dist.panel_tiles())
     else:
         force = system.solve(rows, damping)
     if system.info.lambda_max > 0:  # diagnostics on: backward error of the sharded system
