@@ -673,7 +673,9 @@ def main():
             result["grid"] = spline.predict((h_gx, h_gy))
             result["force"] = spline.force_
 
-        for _ in range(max(1, min(args.warmup, 1))):
+        # two warm-up steps: the sharded predict returns page-locked arrays from torch's caching host allocator, and
+        # with the previous result still referenced while the next is made, two blocks alternate from the third step on
+        for _ in range(max(1, min(args.warmup, 2))):
             api_step()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         e2e_ms = timed(api_step, e2e_steps) / e2e_steps

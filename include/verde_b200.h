@@ -307,6 +307,19 @@ int vb200_block_split(const double *east, const double *north, int64_t n, const 
 int vb200_block_ids(int64_t *ids);
 int vb200_block_aggregate(const double *values, const double *weights, int64_t n, int32_t op,
                           double *out);
+/* Order-free block reduction in ONE pass (no grouping, 24 B read per point and column): every point is labelled
+ * exactly as vb200_block_split labels it and added into dense per-block accumulators with atomics; the non-empty blocks
+ * come back in label order.  op: VB200_REDUCE_SUM / MEAN / COUNT, or WMEAN with weights ([n], applied to every column).
+ * values: [n_columns][n] (n_columns may be 0 for ids / counts only); out_ids: [capacity]; out_values:
+ * [n_columns][capacity] (column c, block j at c * capacity + j); capacity >= min(n, n_east * n_north) always suffices.
+ * Block grids up to 2^26 blocks.  Sums differ from the ordered path (vb200_block_aggregate, pandas' order) by the
+ * rounding order of the additions only; replaces the same reference lines as vb200_block_split + block_aggregate
+ * (verde/blockreduce.py:175-186). */
+int vb200_block_reduce_stream(const double *east, const double *north, int64_t n, const double *centers_east,
+                              int32_t n_east, const double *centers_north, int32_t n_north, const double *values,
+                              int32_t n_columns, const double *weights, int32_t op, int64_t capacity, int64_t *out_ids,
+                              double *out_values, int64_t *n_blocks);
+
 /* distance_mask: replaces verde/mask.py:104-109 (KD-tree nearest-neighbour distance <= maxdist):
  *         mask[i] = 1 when some data point lies within maxdist of (east[i], north[i]), else 0.
  *         mask: n_points bytes, host or device. */

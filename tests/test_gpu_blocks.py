@@ -139,6 +139,62 @@ def test_block_reduce_vs_oracle_shapes(vb, bo, n, shape):
         np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-15)
 
 
+@pytest.mark.parametrize("n,shape", [(1, (1, 1)), (4099, (1, 1)), (70_001, (3, 2)), (20_000, (300, 400)), (400_000, (224, 224))])
+def test_order_free_reduction_matches_the_ordered_path(vb, bo, g, n, shape):
+    """BlockReduce(order_free=True): one pass, atomics into per-block accumulators (vb200_block_reduce_stream).  Blocks,
+    labels and counts are the ordered path's bit for bit; sums may differ by the rounding order of the additions."""
+    rng = np.random.RandomState(n + 7)
+    e, nn, h = rng.uniform(-3, 7, n), rng.uniform(10, 11, n), rng.uniform(0, 100, n)
+    d, d2 = rng.normal(size=n) * 10.0 ** rng.randint(-3, 4, n), rng.uniform(-1, 1, n)
+    w = rng.uniform(0.1, 3, n)
+    region = (-3, 7, 10, 11)
+    kw = dict(shape=shape, region=region)
+    for red, centre in ((np.mean, True), (np.mean, False), (np.sum, False), ("count", True)):
+        want_c, want = vb.BlockReduce(red, center_coordinates=centre, **kw).filter((e, nn), (d, d2))
+        got_c, got = vb.BlockReduce(red, center_coordinates=centre, order_free=True, **kw).filter((e, nn), (d, d2))
+        assert len(got) == 2 and len(got_c) == 2
+        per_block = max(1, n // want[0].size)
+        for a, b in zip(got + got_c, want + want_c):
+            assert a.shape == b.shape
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13 * np.abs(d).max() * (per_block if red is np.sum else 1))
+        if centre:  # block centres of the non-empty blocks: selections, bit exact
+            np.testing.assert_array_equal(got_c[0], want_c[0])
+            np.testing.assert_array_equal(got_c[1], want_c[1])
+        if red == "count":
+            np.testing.assert_array_equal(got[0], want[0])
+    # weighted average, a third coordinate kept (reduced WITHOUT the weights, as the reference does)
+    want_c, want = vb.BlockReduce(np.average, drop_coords=False, **kw).filter((e, nn, h), d, w)
+    got_c, got = vb.BlockReduce(np.average, drop_coords=False, order_free=True, **kw).filter((e, nn, h), d, w)
+    assert len(got_c) == 3
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13 * np.abs(d).max())
+    for a, b in zip(got_c, want_c):
+        np.testing.assert_allclose(a, b, rtol=1e-12)
+    # against the numpy oracle too
+    _, ref_labels = bo.block_split((e, nn), **kw)
+    ids, ref = bo.group_reduce(ref_labels, d, np.mean)
+    _, ids_got, vals = vb.blockreduce.reduce_order_free((e, nn), [d], vb.blockreduce.MEAN, **kw)
+    np.testing.assert_array_equal(ids_got, ids)
+    np.testing.assert_allclose(vals[0], ref, rtol=1e-12, atol=1e-13 * np.abs(d).max())
+    # reductions the one-pass path does not offer take the ordered path, unchanged
+    a = vb.BlockReduce(np.median, order_free=True, **kw).filter((e, nn), d)[1]
+    b = vb.BlockReduce(np.median, **kw).filter((e, nn), d)[1]
+    np.testing.assert_array_equal(a, b)
+
+
+def test_order_free_reduction_abi_errors(vb):
+    import ctypes
+
+    lib = vb._cabi.require_device()
+    e = np.linspace(0, 1, 50)
+    ce, cn = np.array([0.25, 0.75]), np.array([0.5])
+    ids, out, nb = np.empty(1, dtype=np.int64), np.empty(1), ctypes.c_int64()
+    args = (e.ctypes.data, e.ctypes.data, 50, ce.ctypes.data, 2, cn.ctypes.data, 1, e.ctypes.data, 1, None)
+    assert lib.vb200_block_reduce_stream(*args, vb.blockreduce.MEAN, 1, ids.ctypes.data, out.ctypes.data, ctypes.byref(nb)) != 0
+    assert nb.value == 2  # the capacity was too small: the count comes back, the call fails
+    assert lib.vb200_block_reduce_stream(*args, vb.blockreduce.MEDIAN, 2, ids.ctypes.data, out.ctypes.data, ctypes.byref(nb)) != 0
+    assert lib.vb200_block_reduce_stream(*args, vb.blockreduce.WMEAN, 2, ids.ctypes.data, out.ctypes.data, ctypes.byref(nb)) != 0
+
+
 def test_block_reduce_edge_cases(vb, bo):
     # points outside the region go to the nearest (edge) block, like the KD-tree query
     e = np.array([-50.0, 0.2, 0.7, 1.4, 99.0, 0.2])

@@ -97,6 +97,9 @@ SIGNATURES = {
     "vb200_chol_finish": (ctypes.c_int, [ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.POINTER(FitInfo)]),
     "vb200_block_split": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(i64)]),
     "vb200_block_ids": (ctypes.c_int, [ctypes.c_void_p]),
+    "vb200_block_reduce_stream": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                                 ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, i64, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.POINTER(i64)]),
     "vb200_block_aggregate": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, ctypes.c_int32, ctypes.c_void_p]),
     "vb200_distance_mask": (ctypes.c_int, [ctypes.c_void_p] * 2 + [i64, dbl] + [ctypes.c_void_p] * 2 + [i64, ctypes.c_void_p]),
     "vb200_padded_cols": (i64, [i64]),

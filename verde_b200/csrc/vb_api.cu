@@ -1326,6 +1326,60 @@ int vb200_block_aggregate(const double *values, const double *weights, int64_t n
     return 0;
 }
 
+int vb200_block_reduce_stream(const double *east, const double *north, int64_t n, const double *centers_east,
+                              int32_t n_east, const double *centers_north, int32_t n_north, const double *values,
+                              int32_t n_columns, const double *weights, int32_t op, int64_t capacity, int64_t *out_ids,
+                              double *out_values, int64_t *n_blocks)
+{
+    if (n < 0 || n_east < 1 || n_north < 1 || n_columns < 0 || capacity < 0) return fail(VB200_E_BADARG, "bad sizes");
+    const long long nblk = (long long)n_east * n_north;
+    if (nblk > (1LL << 26)) return fail(VB200_E_BADARG, "too many blocks for dense accumulators (limit 2^26): use vb200_block_split");
+    if (op != VB_REDUCE_SUM && op != VB_REDUCE_MEAN && op != VB_REDUCE_COUNT && op != VB_REDUCE_WMEAN)
+        return fail(VB200_E_BADARG, "the one-pass reduction offers sum, mean, count and weighted mean (got %d)", (int)op);
+    if ((op == VB_REDUCE_WMEAN) != (weights != nullptr)) return fail(VB200_E_BADARG, "weights go with VB200_REDUCE_WMEAN, and only with it");
+    if (!n_blocks || !centers_east || !centers_north || (n > 0 && (!east || !north)) || (n_columns > 0 && n > 0 && !values))
+        return fail(VB200_E_BADARG, "null pointer");
+    if (n == 0) {
+        *n_blocks = 0;
+        return 0;
+    }
+    if (!out_ids || (n_columns > 0 && !out_values)) return fail(VB200_E_BADARG, "null pointer");
+    cudaStream_t st = 0;
+    const double *de, *dn, *dce, *dcn, *dv = nullptr, *dw = nullptr;
+    CU(stage_in("in_e", east, n, &de, st));
+    CU(stage_in("in_n", north, n, &dn, st));
+    CU(stage_in("blk_ce", centers_east, n_east, &dce, st));
+    CU(stage_in("blk_cn", centers_north, n_north, &dcn, st));
+    if (n_columns > 0) CU(stage_in("blk_cols", values, (long long)n_columns * n, &dv, st));
+    if (weights) CU(stage_in("in_w", weights, n, &dw, st));
+    unsigned *cnt, *flags, *scratch, *nseg_dev;
+    double *sums, *sumw;
+    CU(ws_get("blk_s_cnt", sizeof(unsigned) * nblk, (void **)&cnt));
+    CU(ws_get("blk_s_flags", sizeof(unsigned) * nblk, (void **)&flags));
+    CU(ws_get("blk_s_scratch", sizeof(unsigned) * (vb_block_scan_scratch_elems(nblk) + 16), (void **)&scratch));
+    CU(ws_get("blk_nseg", sizeof(unsigned), (void **)&nseg_dev));
+    CU(ws_get("blk_s_sums", sizeof(double) * nblk * (n_columns > 0 ? n_columns : 1), (void **)&sums));
+    CU(ws_get("blk_s_sumw", sizeof(double) * nblk, (void **)&sumw));
+    // outputs: device pointers are written in place, host pointers through a staged copy
+    long long *ids_dev;
+    const bool ids_staged = !is_device_ptr(out_ids);
+    if (ids_staged) CU(ws_get("blk_s_ids", sizeof(long long) * (capacity > 0 ? capacity : 1), (void **)&ids_dev));
+    else ids_dev = reinterpret_cast<long long *>(out_ids);
+    OutBuf ob;
+    CU(stage_out("blk_s_out", out_values, (long long)n_columns * capacity, &ob));
+    CU(vb_block_stream(de, dn, n, dce, n_east, dcn, n_north, dv, n_columns, dw, op, cnt, sums, sumw, flags, scratch, nseg_dev,
+                       capacity, ids_dev, ob.dev, st));
+    unsigned nseg = 0;
+    CU(cudaMemcpyAsync(&nseg, nseg_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_blocks = nseg;
+    if ((long long)nseg > capacity) return fail(VB200_E_BADARG, "%u non-empty blocks do not fit the output capacity %lld", nseg, (long long)capacity);
+    if (ids_staged && nseg) CU(cudaMemcpyAsync(out_ids, ids_dev, sizeof(long long) * nseg, cudaMemcpyDeviceToHost, st));
+    CU(finish_out(ob, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int vb200_distance_mask(const double *data_east, const double *data_north, int64_t n, double maxdist,
                         const double *east, const double *north, int64_t n_points, uint8_t *mask)
 {

@@ -546,8 +546,92 @@ int grid_for(long long n)
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
+// order-free ("streaming") block reduction: ONE pass over the points, no grouping
+// ------------------------------------------------------------------------------------------
+// The sort-based path above moves ~68 B per point to give every block its points in pandas' order (needed by the
+// median, by exact reproduction of pandas' summation order, and shared by all columns).  Sums, means, counts and
+// weighted means do not need an order: each point is read once (24 B: easting, northing, value), labelled, and added
+// into dense per-block accumulators with fire-and-forget atomics (RED.ADD.F64 / RED.ADD.U32, resolved in L2: the
+// 224 x 224 accumulators of config 3 are 1 MB), then the non-empty blocks are compacted in label order.  The labels
+// are the bit-exact ones of vb_block_label_kernel; the sums differ from the ordered path only by the rounding order
+// of the additions (and may differ in the last bits from run to run).
+__global__ void __launch_bounds__(256)
+vb_block_stream_kernel(const double *__restrict__ east, const double *__restrict__ north, long long n,
+                       const double *__restrict__ ce, int n_east, const double *__restrict__ cn, int n_north,
+                       const double *__restrict__ values, int ncol, const double *__restrict__ weights,
+                       long long nblk, unsigned *__restrict__ cnt, double *__restrict__ sums, double *__restrict__ sumw)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int je = nearest_centre(__ldcs(east + i), ce, n_east);
+        const int jn = nearest_centre(__ldcs(north + i), cn, n_north);
+        const long long label = (long long)jn * n_east + je;
+        atomicAdd(cnt + label, 1u);
+        double w = 1.0;
+        if (weights) {
+            w = __ldcs(weights + i);
+            atomicAdd(sumw + label, w);
+        }
+        for (int c = 0; c < ncol; ++c) {
+            const double v = __ldcs(values + (long long)c * n + i);
+            atomicAdd(sums + (long long)c * nblk + label, weights ? w * v : v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vb_block_stream_flag_kernel(const unsigned *__restrict__ cnt, long long nblk, unsigned *__restrict__ flags)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblk) flags[b] = cnt[b] ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+vb_block_stream_emit_kernel(const unsigned *__restrict__ cnt, const unsigned *__restrict__ slot, long long nblk,
+                            const double *__restrict__ sums, const double *__restrict__ sumw, int ncol, int op,
+                            long long capacity, long long *__restrict__ ids, double *__restrict__ out)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const unsigned c0 = cnt[b];
+    if (!c0) return;
+    const long long j = slot[b];
+    if (j >= capacity) return;
+    ids[j] = b;
+    for (int c = 0; c < ncol; ++c) {
+        const double s = sums[(long long)c * nblk + b];
+        double r;
+        if (op == VB_REDUCE_SUM) r = s;
+        else if (op == VB_REDUCE_COUNT) r = (double)c0;
+        else if (op == VB_REDUCE_WMEAN) r = s / sumw[b];
+        else r = s / (double)c0;
+        out[(long long)c * capacity + j] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host entry points used by vb_api.cu
 // ------------------------------------------------------------------------------------------
+cudaError_t vb_block_stream(const double *east, const double *north, long long n, const double *ce, int n_east,
+                            const double *cn, int n_north, const double *values, int ncol, const double *weights,
+                            int op, unsigned *cnt, double *sums, double *sumw, unsigned *flags, unsigned *scratch,
+                            unsigned *nseg_dev, long long capacity, long long *ids, double *out, cudaStream_t st)
+{
+    const long long nblk = (long long)n_east * n_north;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(cnt, 0, sizeof(unsigned) * nblk, st)) != cudaSuccess) return e;
+    if (ncol > 0 && (e = cudaMemsetAsync(sums, 0, sizeof(double) * nblk * ncol, st)) != cudaSuccess) return e;
+    if (weights && (e = cudaMemsetAsync(sumw, 0, sizeof(double) * nblk, st)) != cudaSuccess) return e;
+    vb_block_stream_kernel<<<grid_for(n), 256, 0, st>>>(east, north, n, ce, n_east, cn, n_north, values, ncol, weights,
+                                                        nblk, cnt, sums, sumw);
+    const unsigned blocks = (unsigned)((nblk + 255) / 256);
+    vb_block_stream_flag_kernel<<<blocks, 256, 0, st>>>(cnt, nblk, flags);
+    vb_launch_counter += 2;
+    if ((e = scan_u32(flags, nblk, scratch, nseg_dev, st)) != cudaSuccess) return e;
+    vb_block_stream_emit_kernel<<<blocks, 256, 0, st>>>(cnt, flags, nblk, sums, sumw, ncol, op, capacity, ids, out);
+    ++vb_launch_counter;
+    return cudaGetLastError();
+}
+
 long long vb_block_scan_scratch_elems(long long n) { return scan_scratch_elems(n); }
 
 cudaError_t vb_block_split(const double *east, const double *north, long long n, const double *ce, int n_east,

@@ -227,6 +227,12 @@ cudaError_t vb_block_split(const double *east, const double *north, long long n,
                            const double *cn, int n_north, VbBlockWorkspace &ws, long long *labels_dev,
                            cudaStream_t st);
 cudaError_t vb_block_heads(long long n, long long nseg, VbBlockWorkspace &ws, cudaStream_t st);
+// order-free one-pass reduction (sum / mean / count / weighted mean) into dense per-block accumulators; *nseg_dev
+// receives the number of non-empty blocks, ids / out their labels and values [ncol][capacity]
+cudaError_t vb_block_stream(const double *east, const double *north, long long n, const double *ce, int n_east,
+                            const double *cn, int n_north, const double *values, int ncol, const double *weights,
+                            int op, unsigned *cnt, double *sums, double *sumw, unsigned *flags, unsigned *scratch,
+                            unsigned *nseg_dev, long long capacity, long long *ids, double *out, cudaStream_t st);
 cudaError_t vb_block_aggregate(const double *values, const double *weights, long long n, long long nseg, int op,
                                const long long *labels_dev, VbBlockWorkspace &ws, double *out, cudaStream_t st);
 cudaError_t vb_distance_mask(const double *data_e, const double *data_n, long long n, double x0, double y0,
