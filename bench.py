@@ -494,6 +494,9 @@ def main():
                     help="N > 1: replicated m x m Cholesky on every rank, or panel-cyclic over the ranks")
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the end-to-end arm (at most --steps)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-estimator parity block")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="library tunable (vb200_set_option), e.g. chol_lookahead=0 for a launch list whose DMMA launches "
+                         "do not overlap panel kernels (ncu serialises concurrent kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -520,6 +523,11 @@ def main():
     torch.cuda.set_device(local_rank)
     lib = _cabi.require_device()
     lib.vb200_set_device(local_rank)
+    options = {}
+    for item in args.option:
+        key, _, val = item.partition("=")
+        _cabi.check(lib.vb200_set_option(key.encode(), float(val)), "set_option " + item)
+        options[key] = float(val)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints "NCCL version ..." on STDOUT at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
@@ -752,6 +760,8 @@ def main():
                          "note": "A = D G D + damping I (the matrix the reference's Ridge factors); cond_est <= cond_2(A) <= "
                                  "cond_upper; backward_err = ||Js^T W (d - Js c) - damping c|| / (lambda_max ||c|| + ||Js^T W d||)"},
     }
+    if options:
+        line["options"] = options
     if parity is not None:
         line["parity"] = parity
     if not args.no_cpu_baseline and world == 1:

@@ -149,6 +149,7 @@ def test_order_free_reduction_matches_the_ordered_path(vb, bo, g, n, shape):
     w = rng.uniform(0.1, 3, n)
     region = (-3, 7, 10, 11)
     kw = dict(shape=shape, region=region)
+    vb.blockreduce._STREAM_MIN_BLOCKS = 0  # coarse grids too (BlockReduce would route them to the ordered path)
     for red, centre in ((np.mean, True), (np.mean, False), (np.sum, False), ("count", True)):
         want_c, want = vb.BlockReduce(red, center_coordinates=centre, **kw).filter((e, nn), (d, d2))
         got_c, got = vb.BlockReduce(red, center_coordinates=centre, order_free=True, **kw).filter((e, nn), (d, d2))
@@ -175,10 +176,15 @@ def test_order_free_reduction_matches_the_ordered_path(vb, bo, g, n, shape):
     _, ids_got, vals = vb.blockreduce.reduce_order_free((e, nn), [d], vb.blockreduce.MEAN, **kw)
     np.testing.assert_array_equal(ids_got, ids)
     np.testing.assert_allclose(vals[0], ref, rtol=1e-12, atol=1e-13 * np.abs(d).max())
-    # reductions the one-pass path does not offer take the ordered path, unchanged
+    # reductions the one-pass path does not offer take the ordered path, unchanged; so do coarse block grids
+    vb.blockreduce._STREAM_MIN_BLOCKS = 4096
     a = vb.BlockReduce(np.median, order_free=True, **kw).filter((e, nn), d)[1]
     b = vb.BlockReduce(np.median, **kw).filter((e, nn), d)[1]
     np.testing.assert_array_equal(a, b)
+    if shape[0] * shape[1] < 4096:
+        a = vb.BlockReduce(np.mean, order_free=True, **kw).filter((e, nn), d)[1]
+        b = vb.BlockReduce(np.mean, **kw).filter((e, nn), d)[1]
+        np.testing.assert_array_equal(a, b)
 
 
 def test_order_free_reduction_abi_errors(vb):
