@@ -96,6 +96,28 @@ for n in sizes:
     td.all_reduce(flag, op=td.ReduceOp.MIN)
     res["skewed_back_to_back_fits_bit_identical"] = bool(flag.item() == 1.0)
     ok = ok and res["skewed_back_to_back_fits_bit_identical"]
+    if os.environ.get("VB_TEST_IPC_FAILURE"):
+        # CUDA IPC failing on ONE rank (here: simulated on rank 1) must switch EVERY rank to the NCCL exchange
+        real = vb.dist.SharedBuffer
+
+        class Failing(real):
+            def __init__(self, count, dtype):
+                if rank == 1:
+                    raise vb._cabi.EngineError("simulated: cudaIpcGetMemHandle failed")
+                super().__init__(count, dtype)
+
+        vb.dist.SharedBuffer = Failing
+        vb.dist.set_panel_pipeline("peer")
+        other = kernels.GramSystem(n)
+        vb.dist.SharedBuffer = real
+        other.gram.copy_(keep)
+        other.stats.copy_(system.stats)
+        got = other.solve_distributed(n, damping)
+        res["ipc_failure_on_one_rank_falls_back_bit_identical"] = bool(np.array_equal(got, forces["serial"]))
+        got = other.solve_distributed(n, damping) if other.gram.copy_(keep) is not None else None
+        res["ipc_failure_second_fit_bit_identical"] = bool(np.array_equal(got, forces["serial"]))
+        ok = ok and res["ipc_failure_on_one_rank_falls_back_bit_identical"] and res["ipc_failure_second_fit_bit_identical"]
+        del other
     mine = torch.from_numpy(forces["peer"]).cuda()
     lo, hi = mine.clone(), mine.clone()
     td.all_reduce(lo, op=td.ReduceOp.MIN); td.all_reduce(hi, op=td.ReduceOp.MAX)

@@ -218,7 +218,10 @@ class PeerWindow:
     """
     ``window.ptr(r, name)``: device address, valid on THIS rank's GPU, of rank r's ``SharedBuffer`` *name* -- the
     peers' buffers mapped into this process in this rank's own device context (``vb200_shared_open``), so that copies
-    into them are NVLink peer writes done by this GPU's copy engines.  Construction is collective.
+    into them are NVLink peer writes done by this GPU's copy engines.  Construction is collective (one
+    ``all_gather_object``); a mapping that fails (no peer access between two GPUs, CUDA IPC unavailable in the
+    container) is remembered in ``self.error`` instead of raised, so that the caller can make the decision to fall
+    back collective (``agree_on_status``) -- a rank that raised here would strand the others.
     """
 
     def __init__(self, buffers):
@@ -235,15 +238,20 @@ class PeerWindow:
         everyone = [None] * size
         td.all_gather_object(everyone, mine)
         self._ptr = {}
+        self.error = None
         for r, entry in enumerate(everyone):
-            for name, handle in entry.items():
+            for name, handle in (entry or {}).items():
                 if r == rank:
                     self._ptr[(r, name)] = self.local[name].ptr
-                else:
+                elif self.error is None:
                     ptr = ctypes.c_void_p()
-                    _cabi.check(lib.vb200_shared_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)), "shared_open")
-                    self._ptr[(r, name)] = int(ptr.value)
-        td.barrier()
+                    rc = lib.vb200_shared_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr))
+                    if rc != 0:
+                        self.error = _cabi.load().vb200_last_error().decode("utf-8", "replace")
+                    else:
+                        self._ptr[(r, name)] = int(ptr.value)
+        if any(not entry for entry in everyone):
+            self.error = self.error or "a peer has no shareable buffers"
 
     def ptr(self, r, name):
         return self._ptr[(r, name)]

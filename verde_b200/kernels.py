@@ -22,6 +22,7 @@ fit_spline / fit_spline_2d   verde/spline.py:462-463 / verde/vector.py:287-288
 Everything executes in ``libverde_b200.so`` on the current CUDA device.
 """
 import ctypes
+import warnings
 from warnings import warn
 
 import numpy as np
@@ -239,13 +240,21 @@ class GramSystem:
         if peer_exchange:
             # the matrix and the per-panel flag words live in CUDA-IPC-exportable allocations: the other ranks map
             # them (PeerWindow, at the first panel-cyclic factorisation) and push factored panels straight into them
-            self._shared = {"gram": dist.SharedBuffer(count, torch.float64), "flags": dist.SharedBuffer(4096, torch.int64)}
+            try:
+                self._shared = {"gram": dist.SharedBuffer(count, torch.float64), "flags": dist.SharedBuffer(4096, torch.int64)}
+            except _cabi.EngineError as exc:
+                # CUDA IPC is not available here: plain memory; the first factorisation makes the fall-back to the
+                # NCCL exchange collective (this rank then reports "no shareable buffers" to its peers)
+                warnings.warn("peer-memory panel exchange unavailable ({}): using ncclBroadcast".format(exc))
+                self._shared = None
+        if self._shared is not None:
             self.gram = self._shared["gram"].tensor
             self._flags = self._shared["flags"].tensor
             self._flags.zero_()
             self._epoch_src = torch.zeros(1, dtype=torch.int64, device=dev)
         else:
             self.gram = torch.empty(count, dtype=torch.float64, device=dev)
+        self._wants_peer = bool(peer_exchange)  # was built for the peer exchange (even if the allocation failed)
         self.stats = torch.empty(self._lib.vb200_stats_doubles(self.cols), dtype=torch.float64, device=dev)
         self.info = _cabi.FitInfo()
         self._torch = torch
@@ -353,13 +362,23 @@ class GramSystem:
             return lib.vb200_chol_update_ranges(gram_ptr, cols, k0, width, len(owned), los, his)
 
         pipeline = dist.panel_pipeline() if len(schedule) > 1 else "serial"
-        if pipeline == "peer" and self._shared is None:
-            pipeline = "lookahead"  # this matrix was not allocated for the peer exchange
+        if pipeline == "peer" and not self._wants_peer:
+            pipeline = "lookahead"  # this matrix was not allocated for the peer exchange (the same on every rank)
+        if pipeline == "peer" and self._window is None:
+            # first factorisation on this matrix: map the peers' buffers.  Whether that worked is agreed on by all
+            # ranks (a failed mapping or allocation on ONE rank switches EVERY rank to the NCCL exchange, for good).
+            window = dist.PeerWindow(self._shared or {})
+            lowest, _ = dist.agree_on_status(-1 if window.error else 0)
+            if lowest < 0:
+                if window.error:
+                    warnings.warn("peer-memory panel exchange unavailable ({}): using ncclBroadcast".format(window.error))
+                self._wants_peer = False
+                pipeline = "lookahead"
+            else:
+                self._window = window
         if pipeline == "peer":
             # Look-ahead order + peer-memory pushes: see dist.set_panel_pipeline.  flags[p] on every rank is written
             # by the owner of panel p (the fit's epoch) after the panel itself has landed in this rank's matrix.
-            if self._window is None:
-                self._window = dist.PeerWindow(self._shared)
             ready_base = self._flags.numel() - 1024  # flags[ready_base + r]: rank r's matrix is ready to receive
             if len(schedule) > ready_base or size > 1024:
                 raise ValueError("too many outer panels for the peer exchange ({})".format(len(schedule)))
