@@ -910,18 +910,26 @@ int vb200_gram_solve_multi(const double *gram_dev, const double *stats_dev, int6
     const long long stride = vb200_gram_doubles(cols);
     // how many factors fit side by side: at most 60 % of what is free (the workspace is cached, and the
     // caller still needs room for its own tensors, panels and predict scratch afterwards)
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
+    long long want = n_dampings > 64 ? 64 : n_dampings;
+    if (g_opt.sweep_group > 0 && want > g_opt.sweep_group) want = g_opt.sweep_group;
+    size_t cached_b = 0;
     {
         int dev = 0;
         CU(cudaGetDevice(&dev));
         auto it = g_ws.find(std::to_string(dev) + ":chol_batch");
-        if (it != g_ws.end()) free_b += it->second.bytes;  // re-usable
+        if (it != g_ws.end()) cached_b = it->second.bytes;  // re-usable
     }
-    long long group = (long long)((size_t)(0.6 * (double)free_b) / (sizeof(double) * (size_t)stride));
-    if (group > n_dampings) group = n_dampings;
-    if (group > 64) group = 64;
-    if (g_opt.sweep_group > 0 && group > g_opt.sweep_group) group = g_opt.sweep_group;
+    long long group = want;
+    if (cached_b < sizeof(double) * (size_t)stride * (size_t)want) {
+        // the cached batch workspace does not hold the whole sweep yet: ask the driver what is free (cudaMemGetInfo
+        // costs milliseconds on a 180 GB device, so a sweep whose workspace already exists -- every (fold, mindist)
+        // job of a SplineCV after the first -- does not ask again)
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        free_b += cached_b;
+        group = (long long)((size_t)(0.6 * (double)free_b) / (sizeof(double) * (size_t)stride));
+        if (group > want) group = want;
+    }
     if (group < 1) return fail(VB200_E_NOMEM, "not enough device memory for one %lld x %lld factor", (long long)cols, (long long)cols);
     double *Lb, *inv_scale, *rhs, *xb, *damp_dev, *mm;
     int *d_info, *d_flags;
