@@ -191,8 +191,9 @@ def next_epoch():
 class SharedBuffer:
     """
     A device buffer of this rank that the other ranks of the node can map (``vb200_shared_alloc``: cudaMalloc +
-    CUDA-IPC handle), wrapped as a torch tensor without copying.  Never freed before the process ends: the peers keep
-    it mapped (``PeerWindow``), and CUDA forbids freeing exported memory that is still mapped elsewhere.
+    CUDA-IPC handle), wrapped as a torch tensor without copying.  CUDA forbids freeing exported memory that is still
+    mapped elsewhere, so ``free`` is only called (``GramSystem.release``) after every peer has closed its mapping
+    (``PeerWindow.close``, then a barrier) or when no peer ever mapped it.
     """
 
     def __init__(self, count, dtype):
@@ -212,6 +213,17 @@ class SharedBuffer:
         typestr = {torch.float64: "<f8", torch.int64: "<i8"}[dtype]
         self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (self.ptr, False), "version": 2}
         self.tensor = torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def free(self):
+        "cudaFree (idempotent).  The caller guarantees that no tensor view and no peer mapping is used afterwards."
+        from . import _cabi
+
+        if self.ptr:
+            import ctypes
+
+            self.tensor = None
+            _cabi.load().vb200_shared_free(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 class PeerWindow:
@@ -255,6 +267,19 @@ class PeerWindow:
 
     def ptr(self, r, name):
         return self._ptr[(r, name)]
+
+    def close(self):
+        "Unmap the peers' buffers from this process (local; the owners free them after a barrier)."
+        import ctypes
+
+        from . import _cabi
+
+        rank, _ = world()
+        lib = _cabi.load()
+        for (r, _name), address in list(self._ptr.items()):
+            if r != rank:
+                lib.vb200_shared_close(ctypes.c_void_p(address))
+        self._ptr = {}
 
 
 def comm_stream():

@@ -236,7 +236,10 @@ class GramSystem:
         count = self._lib.vb200_gram_doubles(self.cols)
         self._shared = None
         if peer_exchange is None:
-            peer_exchange = dist.world()[1] > 1 and dist.backend() == "nccl" and dist.panel_pipeline() == "peer"
+            # only systems that will be factored panel-cyclically need exportable memory (identical on every rank:
+            # the rule depends on sizes alone)
+            peer_exchange = (dist.world()[1] > 1 and dist.backend() == "nccl" and dist.panel_pipeline() == "peer"
+                             and dist.use_distributed_cholesky((self.cols + 127) // 128, dist.panel_tiles()))
         if peer_exchange:
             # the matrix and the per-panel flag words live in CUDA-IPC-exportable allocations: the other ranks map
             # them (PeerWindow, at the first panel-cyclic factorisation) and push factored panels straight into them
@@ -259,6 +262,39 @@ class GramSystem:
         self.info = _cabi.FitInfo()
         self._torch = torch
         self._window = None  # dist.PeerWindow onto the other ranks' (gram, flags), made by the first peer-mode factorisation
+
+    def release(self):
+        """
+        Give the CUDA-IPC allocations back.  COLLECTIVE when peers have mapped them (every rank calls it at the same
+        point: unmap the peers' buffers, barrier, free the own ones); local otherwise.  The object is unusable after.
+        """
+        from . import dist
+
+        if self._shared is None:
+            return
+        if self._window is not None:
+            self._torch.cuda.synchronize()
+            self._window.close()
+            self._window = None
+            import torch.distributed as td
+
+            td.barrier()
+        self.gram = self._flags = None
+        for buf in self._shared.values():
+            buf.free()
+        self._shared = None
+
+    def __del__(self):
+        # never mapped by a peer (no panel-cyclic factorisation ran on it): the exported memory can go now; a mapped
+        # one is only freed by the collective release() -- dropping it silently would strand the peers' mappings
+        try:
+            if getattr(self, "_shared", None) is not None and getattr(self, "_window", None) is None:
+                self.gram = self._flags = None
+                for buf in self._shared.values():
+                    buf.free()
+                self._shared = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def accumulate(self, kind, east, north, data, weights, force_east, force_north, mindist,
                    poisson=0.0, accumulate=False):
@@ -606,7 +642,11 @@ def _shared_system(cols):
     key = (torch.cuda.current_device(), int(cols))
     system = _SHARED_SYSTEM.get(key)
     if system is None:
-        _SHARED_SYSTEM.clear()  # a different size: let the old matrix go first
+        # a different size: let the old matrix go first (collective when its peers mapped it -- every rank is here
+        # with the same sizes in the same order)
+        for old in _SHARED_SYSTEM.values():
+            old.release()
+        _SHARED_SYSTEM.clear()
         system = _SHARED_SYSTEM[key] = GramSystem(cols)
     system.info = _cabi.FitInfo()
     return system
