@@ -492,10 +492,14 @@ class GramSystem:
             if rank == schedule[0][2]:
                 status = lib.vb200_chol_panel(gram_ptr, cols, schedule[0][0], schedule[0][1])
             ready.record(main)
+            # EVERY rank orders its side stream behind vb200_chol_begin (and, on the owner, the first panel): that call
+            # rewrites the whole matrix in place, and a panel received before it has finished here would be scaled
+            # again (found by the skew test of tools/run_dist_pipeline.py; invisible between barriers)
+            comm.wait_event(ready)
             mark("panel")
             for p, (k0, width, owner) in enumerate(schedule):
                 lib.vb200_chol_panel_range(cols, k0, width, ctypes.byref(offset), ctypes.byref(count))
-                if rank == owner:
+                if rank == owner and p > 0:
                     comm.wait_event(ready)  # the panel is factored
                 with torch.cuda.stream(comm):
                     dist.broadcast_(self.gram[offset.value:offset.value + count.value], owner)
