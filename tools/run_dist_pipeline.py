@@ -77,6 +77,7 @@ for n in sizes:
     skew_ok = True
     for rep in range(6 if os.environ.get("VB_SKEW_WITHOUT_HANDSHAKE") else 4):
         vb.dist._READY_HANDSHAKE = rep < 4  # reps 4, 5 (opt-in): the race the handshake closes, made likely by the skew
+        vb.dist.set_panel_pipeline("lookahead" if rep in (2, 3) else "peer")  # both asynchronous schedules
         system.info = vb._cabi.FitInfo()
         system.gram.copy_(keep)
         if (rank + rep) % 2:
@@ -92,6 +93,7 @@ for n in sizes:
         else:
             res["without_handshake_rep%d_bit_identical_on_rank0" % rep] = same
     vb.dist._READY_HANDSHAKE = True
+    vb.dist.set_panel_pipeline("peer")
     flag = torch.tensor([1.0 if skew_ok else 0.0], device="cuda")
     td.all_reduce(flag, op=td.ReduceOp.MIN)
     res["skewed_back_to_back_fits_bit_identical"] = bool(flag.item() == 1.0)
