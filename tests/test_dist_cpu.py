@@ -85,6 +85,36 @@ def _worker(rank, world, port, out_dir):
                 j0, j1 = q0 * blk, (q0 + qwidth) * blk
                 mat[j0:, j0:j1] -= mat[j0:, c0:c1] @ mat[j0:j1, c0:c1].T
     np.testing.assert_allclose(np.tril(mat), np.linalg.cholesky(a_full), rtol=0, atol=1e-10)
+    # 4b. the LOOK-AHEAD order of GramSystem.solve_distributed (the owner of panel p+1 updates and factors it first,
+    #     as soon as panel p has arrived; everything else it owns is updated afterwards through dist.owned_ranges)
+    work = torch.from_numpy(a_full.copy())
+    mat = work.numpy()
+
+    def factor(c0, c1):
+        mat[c0:c1, c0:c1] = np.linalg.cholesky(mat[c0:c1, c0:c1])
+        mat[c1:, c0:c1] = np.linalg.solve(mat[c0:c1, c0:c1], mat[c1:, c0:c1].T).T
+
+    def update(c0, c1, j0, j1):
+        mat[j0:, j0:j1] -= mat[j0:, c0:c1] @ mat[j0:j1, c0:c1].T
+
+    if rank == schedule[0][2]:
+        factor(0, schedule[0][1] * blk)
+    for p, (k0, width, owner) in enumerate(schedule):
+        c0, c1 = k0 * blk, (k0 + width) * blk
+        panel = work[:, c0:c1].contiguous()
+        dist.broadcast_(panel, owner)
+        work[:, c0:c1] = panel
+        later = schedule[p + 1:]
+        if later and later[0][2] == rank:
+            q0, qwidth, _ = later[0]
+            update(c0, c1, q0 * blk, (q0 + qwidth) * blk)
+            factor(q0 * blk, (q0 + qwidth) * blk)
+            later = later[1:]
+        for lo, hi in dist.owned_ranges(later, rank):
+            update(c0, c1, lo * blk, hi * blk)
+    np.testing.assert_allclose(np.tril(mat), np.linalg.cholesky(a_full), rtol=0, atol=1e-10)
+    assert dist.owned_ranges(schedule, 0) == [(0, 3), (6, 9)] and dist.owned_ranges(schedule[1:], 1) == [(3, 6), (9, 11)]
+    assert dist.panel_tiles(2) == 8 and dist.panel_tiles(4) == 4 and dist.panel_tiles(8) == 4
     assert dist.use_distributed_cholesky(391, 8) and not dist.use_distributed_cholesky(24, 8)
     dist.set_cholesky("replicated")
     assert not dist.use_distributed_cholesky(391, 8)
@@ -121,6 +151,15 @@ def test_shard_bounds_cover_everything():
         dist.set_sharding("maybe")
     with pytest.raises(ValueError):
         dist.set_cholesky("sometimes")
+    assert len(dist.panel_cyclic_schedule(392, 4, 8)) == 98 and dist.panel_tiles(1) == 8
+    for mode in ("serial", "lookahead", "peer"):
+        dist.set_panel_pipeline(mode)
+        assert dist.panel_pipeline() == mode
+    with pytest.raises(ValueError):
+        dist.set_panel_pipeline("eager")
+    dist.set_merged_updates(False)
+    assert not dist.merged_updates()
+    dist.set_merged_updates(True)
     sched = dist.panel_cyclic_schedule(391, 8, 8)
     assert len(sched) == 49 and sched[0] == (0, 8, 0) and sched[-1] == (384, 7, 0) and sched[9] == (72, 8, 1)
     assert sum(w for _, w, _ in sched) == 391

@@ -122,6 +122,11 @@ def panel_tiles(size=None):
     return 4 if size >= 4 else 8
 
 
+def owned_ranges(panels, rank):
+    "Block-column ranges [lo, hi) of the panels in *panels* (schedule entries) that *rank* owns, ascending."
+    return [(q0, q0 + qwidth) for q0, qwidth, qowner in panels if qowner == rank]
+
+
 def use_distributed_cholesky(block_rows, panel_tiles, size=None):
     "Decision rule of ``set_cholesky``; identical on every rank (it only depends on sizes)."
     if size is None:

@@ -384,7 +384,7 @@ class GramSystem:
 
         def update_owned(k0, width, panels):
             "apply panel [k0, k0 + width) to the later panels this rank owns: ONE launch over all their block columns"
-            owned = [(q0, q0 + qwidth) for q0, qwidth, qowner in panels if qowner == rank]
+            owned = dist.owned_ranges(panels, rank)
             if not owned:
                 return 0
             if not dist.merged_updates():
