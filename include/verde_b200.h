@@ -69,7 +69,7 @@ typedef struct vb200_fit_info {
     double sigma_min_kept;
     int32_t power_its;       /* iterations the condition estimate took: power (lambda_max) / inverse (lambda_min) */
     int32_t inverse_its;
-    /* --- look-ahead Cholesky: DMMA launches that ran BESIDE the factorisation of the next panel (on SMs - R of the
+    /* --- since ABI version 201.  Look-ahead Cholesky: DMMA launches that ran BESIDE the factorisation of the next panel (on SMs - R of the
      * SMs, joined later by a second grid on the same tile queue).  Their event spans time a kernel that owns only part
      * of the machine, so they are reported apart from gemm_ms / gemm_flops (the roofline figures). --- */
     double shared_gemm_ms;
@@ -78,6 +78,8 @@ typedef struct vb200_fit_info {
 } vb200_fit_info;
 
 /* ---- library / device -------------------------------------------------------------- */
+/* 201: vb200_fit_info grew shared_gemm_*; added vb200_get_option, vb200_chol_update_ranges, vb200_shared_*,
+ * vb200_peer_copy_async, vb200_chol_wait_panel, vb200_stream_wait_flag, vb200_block_reduce_stream */
 int vb200_version(void);
 const char *vb200_last_error(void);
 int vb200_device_count(void);

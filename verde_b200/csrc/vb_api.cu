@@ -446,7 +446,7 @@ cudaError_t vb_gemm_dispatch(const VbGemmParams &p, cudaStream_t st) { return ti
 
 extern "C" {
 
-int vb200_version(void) { return 200; }
+int vb200_version(void) { return 201; }
 const char *vb200_last_error(void) { return g_error.c_str(); }
 
 int vb200_device_count(void)
