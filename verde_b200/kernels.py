@@ -408,6 +408,7 @@ class GramSystem:
             if lowest < 0:
                 if window.error:
                     warnings.warn("peer-memory panel exchange unavailable ({}): using ncclBroadcast".format(window.error))
+                window.close()  # whatever this rank did map must not outlive the decision
                 self._wants_peer = False
                 pipeline = "lookahead"
             else:
