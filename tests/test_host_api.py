@@ -27,6 +27,19 @@ def test_constructor_signatures_and_clone():
     assert vs.get_params() == {"poisson": 0.5, "mindist": 10e3, "damping": None, "force_coords": None, "engine": "auto"}
     cv = vb.SplineCV()
     assert cv.mindists == [0] and cv.dampings == (1e-10, 1e-5, 1e-1) and cv.cv is None and cv.scoring is None
+    # BlockReduce: the reference's parameters plus the opt-in one-pass flavour (off by default -> a drop-in)
+    br = vb.BlockReduce(np.mean, spacing=2.0)
+    assert br.get_params() == {"reduction": np.mean, "spacing": 2.0, "region": None, "adjust": "spacing",
+                               "center_coordinates": False, "shape": None, "drop_coords": True, "order_free": False}
+    assert clone(vb.BlockReduce(np.sum, shape=(3, 4), order_free=True)).order_free is True
+    assert vb.BlockMean(spacing=2.0).get_params()["uncertainty"] is False and vb.BlockMean(spacing=2.0).order_free is False
+    from verde_b200 import blockreduce
+
+    assert blockreduce.reduction_code(np.mean) in blockreduce._STREAM_OPS
+    assert blockreduce.reduction_code(np.median) not in blockreduce._STREAM_OPS
+    assert blockreduce.reduction_code(np.average, weighted=True) == blockreduce.WMEAN
+    with pytest.raises(NotImplementedError):
+        blockreduce.reduction_code(lambda v: v.max() - v.min())
 
 
 def test_deprecation_warnings_match_reference():
